@@ -1,0 +1,490 @@
+// BN254 arithmetic for the sm_100a verification kernels: Fp (8 x 32-bit Montgomery limbs, PTX carry
+// chains from fp_ptx.cuh), the Fp2/Fp6/Fp12 tower, G1/G2 group law, optimal-ate line functions and
+// the final exponentiation.  This is the arithmetic the reference obtains from the EVM precompiles
+// ecAdd/ecMul/ecPairing (/root/reference/contracts/src/common/groth16.rs:12-14,54-55,121-125).
+//
+// The same source also compiles as plain C++ (tests/host_emu) with a portable Fp backend so the
+// tower / curve / pairing logic can be checked on a CPU-only box; the library itself never takes
+// that path: every exported entry point launches CUDA kernels.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ZKV_HD __host__ __device__
+#define ZKV_INLINE __forceinline__
+#define ZKV_NOINLINE __noinline__
+#define ZKV_CONST static __device__ __constant__ const
+#else
+#define ZKV_HD
+#define ZKV_INLINE inline
+#define ZKV_NOINLINE
+#define ZKV_CONST static const
+#endif
+
+#include "bn254_consts.cuh"
+#if defined(__CUDACC__)
+#include "fp_ptx.cuh"
+#endif
+
+namespace zkv {
+
+struct alignas(16) fp { uint32_t v[8]; };
+struct fp2 { fp c0, c1; };
+struct fp6 { fp2 c0, c1, c2; };
+struct fp12 { fp6 c0, c1; };
+
+// ------------------------------------------------------------------------------------------ Fp
+ZKV_HD ZKV_INLINE fp fp_const(const uint32_t* c) { fp r; for (int i = 0; i < 8; i++) r.v[i] = c[i]; return r; }
+ZKV_HD ZKV_INLINE fp fp_zero() { fp r; for (int i = 0; i < 8; i++) r.v[i] = 0; return r; }
+ZKV_HD ZKV_INLINE fp fp_one() { return fp_const(C_ONE); }
+ZKV_HD ZKV_INLINE bool fp_is_zero(const fp& a) { uint32_t t = 0; for (int i = 0; i < 8; i++) t |= a.v[i]; return t == 0; }
+ZKV_HD ZKV_INLINE bool fp_eq(const fp& a, const fp& b) { uint32_t t = 0; for (int i = 0; i < 8; i++) t |= a.v[i] ^ b.v[i]; return t == 0; }
+// raw (non-Montgomery) 256-bit compare a >= m
+ZKV_HD ZKV_INLINE bool u256_geq(const uint32_t* a, const uint32_t* m) {
+    uint32_t borrow = 0;
+    for (int i = 0; i < 8; i++) { uint64_t t = (uint64_t)a[i] - m[i] - borrow; borrow = (uint32_t)(t >> 63); }
+    return borrow == 0;
+}
+
+#if defined(__CUDA_ARCH__)
+ZKV_HD ZKV_INLINE void fp_mul(fp& r, const fp& a, const fp& b) { fp_mul_ptx(r.v, a.v, b.v); }
+ZKV_HD ZKV_INLINE void fp_add(fp& r, const fp& a, const fp& b) { fp_add_ptx(r.v, a.v, b.v); }
+ZKV_HD ZKV_INLINE void fp_sub(fp& r, const fp& a, const fp& b) { fp_sub_ptx(r.v, a.v, b.v); }
+#else
+// portable backend (host emulation for tests only)
+ZKV_HD inline void fp_mul(fp& r, const fp& a, const fp& b) {
+    uint32_t t[10] = {0};
+    for (int i = 0; i < 8; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < 8; j++) { c += (uint64_t)a.v[j] * b.v[i] + t[j]; t[j] = (uint32_t)c; c >>= 32; }
+        c += t[8]; t[8] = (uint32_t)c; t[9] = (uint32_t)(c >> 32);
+        uint32_t m = t[0] * 0xe4866389u;
+        c = (uint64_t)m * C_P[0] + t[0]; c >>= 32;
+        for (int j = 1; j < 8; j++) { c += (uint64_t)m * C_P[j] + t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
+        c += t[8]; t[7] = (uint32_t)c; t[8] = t[9] + (uint32_t)(c >> 32);
+    }
+    if (t[8] || u256_geq(t, C_P)) { uint32_t bo = 0; for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)t[i] - C_P[i] - bo; r.v[i] = (uint32_t)d; bo = (uint32_t)(d >> 63); } }
+    else for (int i = 0; i < 8; i++) r.v[i] = t[i];
+}
+ZKV_HD inline void fp_add(fp& r, const fp& a, const fp& b) {
+    uint32_t t[8]; uint64_t c = 0;
+    for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + b.v[i]; t[i] = (uint32_t)c; c >>= 32; }
+    if (u256_geq(t, C_P)) { uint32_t bo = 0; for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)t[i] - C_P[i] - bo; r.v[i] = (uint32_t)d; bo = (uint32_t)(d >> 63); } }
+    else for (int i = 0; i < 8; i++) r.v[i] = t[i];
+}
+ZKV_HD inline void fp_sub(fp& r, const fp& a, const fp& b) {
+    uint32_t t[8]; uint32_t bo = 0;
+    for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)a.v[i] - b.v[i] - bo; t[i] = (uint32_t)d; bo = (uint32_t)(d >> 63); }
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) { c += (uint64_t)t[i] + (bo ? C_P[i] : 0); r.v[i] = (uint32_t)c; c >>= 32; }
+}
+#endif
+ZKV_HD ZKV_INLINE void fp_sqr(fp& r, const fp& a) { fp_mul(r, a, a); }
+ZKV_HD ZKV_INLINE void fp_dbl(fp& r, const fp& a) { fp_add(r, a, a); }
+ZKV_HD ZKV_INLINE void fp_neg(fp& r, const fp& a) { fp z = fp_zero(); fp_sub(r, z, a); }
+ZKV_HD ZKV_INLINE void fp_half(fp& r, const fp& a) {
+    uint32_t odd = 0u - (a.v[0] & 1u);
+    uint32_t t[8]; uint64_t c = 0;
+    for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + (C_P[i] & odd); t[i] = (uint32_t)c; c >>= 32; }
+    for (int i = 0; i < 7; i++) r.v[i] = (t[i] >> 1) | (t[i + 1] << 31);
+    r.v[7] = t[7] >> 1;   // a + p < 2^255: no carry out
+}
+ZKV_HD ZKV_INLINE void fp_to_mont(fp& r, const fp& a) { fp r2 = fp_const(C_R2); fp_mul(r, a, r2); }
+ZKV_HD ZKV_INLINE void fp_from_mont(fp& r, const fp& a) { fp one = fp_zero(); one.v[0] = 1; fp_mul(r, a, one); }
+// a^(p-2); inv(0) = 0
+ZKV_HD ZKV_NOINLINE void fp_inv(fp& r, const fp& a) {
+    fp acc = fp_one(), base = a;
+    for (int i = 253; i >= 0; i--) {
+        fp_sqr(acc, acc);
+        if ((C_PM2[i >> 5] >> (i & 31)) & 1) fp_mul(acc, acc, base);
+    }
+    r = acc;
+}
+
+// ------------------------------------------------------------------------------------------ Fp2 = Fp[u]/(u^2+1)
+ZKV_HD ZKV_INLINE fp2 f2_zero() { fp2 r; r.c0 = fp_zero(); r.c1 = fp_zero(); return r; }
+ZKV_HD ZKV_INLINE fp2 f2_one() { fp2 r; r.c0 = fp_one(); r.c1 = fp_zero(); return r; }
+ZKV_HD ZKV_INLINE fp2 f2_const(const uint32_t c[2][8]) { fp2 r; r.c0 = fp_const(c[0]); r.c1 = fp_const(c[1]); return r; }
+ZKV_HD ZKV_INLINE bool f2_is_zero(const fp2& a) { return fp_is_zero(a.c0) & fp_is_zero(a.c1); }
+ZKV_HD ZKV_INLINE bool f2_eq(const fp2& a, const fp2& b) { return fp_eq(a.c0, b.c0) & fp_eq(a.c1, b.c1); }
+ZKV_HD ZKV_INLINE void f2_add(fp2& r, const fp2& a, const fp2& b) { fp_add(r.c0, a.c0, b.c0); fp_add(r.c1, a.c1, b.c1); }
+ZKV_HD ZKV_INLINE void f2_sub(fp2& r, const fp2& a, const fp2& b) { fp_sub(r.c0, a.c0, b.c0); fp_sub(r.c1, a.c1, b.c1); }
+ZKV_HD ZKV_INLINE void f2_neg(fp2& r, const fp2& a) { fp_neg(r.c0, a.c0); fp_neg(r.c1, a.c1); }
+ZKV_HD ZKV_INLINE void f2_dbl(fp2& r, const fp2& a) { fp_dbl(r.c0, a.c0); fp_dbl(r.c1, a.c1); }
+ZKV_HD ZKV_INLINE void f2_half(fp2& r, const fp2& a) { fp_half(r.c0, a.c0); fp_half(r.c1, a.c1); }
+ZKV_HD ZKV_INLINE void f2_conj(fp2& r, const fp2& a) { r.c0 = a.c0; fp_neg(r.c1, a.c1); }
+ZKV_HD ZKV_NOINLINE void f2_mul(fp2& r, const fp2& a, const fp2& b) {
+    fp t0, t1, t2, s0, s1;
+    fp_mul(t0, a.c0, b.c0); fp_mul(t1, a.c1, b.c1);
+    fp_add(s0, a.c0, a.c1); fp_add(s1, b.c0, b.c1);
+    fp_mul(t2, s0, s1);
+    fp_sub(r.c0, t0, t1);
+    fp_sub(t2, t2, t0); fp_sub(r.c1, t2, t1);
+}
+ZKV_HD ZKV_NOINLINE void f2_sqr(fp2& r, const fp2& a) {
+    fp s, d, m;
+    fp_add(s, a.c0, a.c1); fp_sub(d, a.c0, a.c1); fp_mul(m, a.c0, a.c1);
+    fp_mul(r.c0, s, d); fp_dbl(r.c1, m);
+}
+ZKV_HD ZKV_NOINLINE void f2_mul_fp(fp2& r, const fp2& a, const fp& k) { fp_mul(r.c0, a.c0, k); fp_mul(r.c1, a.c1, k); }
+// (9+u)(a0 + a1 u) = (9 a0 - a1) + (9 a1 + a0) u
+ZKV_HD ZKV_NOINLINE void f2_mul_xi(fp2& r, const fp2& a) {
+    fp t0, t1;
+    fp_dbl(t0, a.c0); fp_dbl(t0, t0); fp_dbl(t0, t0); fp_add(t0, t0, a.c0);
+    fp_dbl(t1, a.c1); fp_dbl(t1, t1); fp_dbl(t1, t1); fp_add(t1, t1, a.c1);
+    fp n0, n1; fp_sub(n0, t0, a.c1); fp_add(n1, t1, a.c0);
+    r.c0 = n0; r.c1 = n1;
+}
+ZKV_HD ZKV_NOINLINE void f2_inv(fp2& r, const fp2& a) {
+    fp n, t;
+    fp_sqr(n, a.c0); fp_sqr(t, a.c1); fp_add(n, n, t); fp_inv(n, n);
+    fp_mul(r.c0, a.c0, n); fp_mul(t, a.c1, n); fp_neg(r.c1, t);
+}
+
+// ------------------------------------------------------------------------------------------ Fp6 = Fp2[v]/(v^3 - xi)
+ZKV_HD ZKV_INLINE void f6_add(fp6& r, const fp6& a, const fp6& b) { f2_add(r.c0, a.c0, b.c0); f2_add(r.c1, a.c1, b.c1); f2_add(r.c2, a.c2, b.c2); }
+ZKV_HD ZKV_INLINE void f6_sub(fp6& r, const fp6& a, const fp6& b) { f2_sub(r.c0, a.c0, b.c0); f2_sub(r.c1, a.c1, b.c1); f2_sub(r.c2, a.c2, b.c2); }
+ZKV_HD ZKV_INLINE void f6_neg(fp6& r, const fp6& a) { f2_neg(r.c0, a.c0); f2_neg(r.c1, a.c1); f2_neg(r.c2, a.c2); }
+ZKV_HD ZKV_INLINE void f6_mul_v(fp6& r, const fp6& a) { fp2 t; f2_mul_xi(t, a.c2); r.c2 = a.c1; r.c1 = a.c0; r.c0 = t; }
+ZKV_HD ZKV_NOINLINE void f6_mul(fp6& r, const fp6& a, const fp6& b) {
+    fp2 v0, v1, v2, t0, t1, t2, x0, x1;
+    f2_mul(v0, a.c0, b.c0); f2_mul(v1, a.c1, b.c1); f2_mul(v2, a.c2, b.c2);
+    f2_add(t0, a.c1, a.c2); f2_add(t1, b.c1, b.c2); f2_mul(t2, t0, t1);
+    f2_sub(t2, t2, v1); f2_sub(t2, t2, v2); f2_mul_xi(t2, t2); f2_add(x0, t2, v0);
+    f2_add(t0, a.c0, a.c1); f2_add(t1, b.c0, b.c1); f2_mul(t2, t0, t1);
+    f2_sub(t2, t2, v0); f2_sub(t2, t2, v1); f2_mul_xi(t0, v2); f2_add(x1, t2, t0);
+    f2_add(t0, a.c0, a.c2); f2_add(t1, b.c0, b.c2); f2_mul(t2, t0, t1);
+    f2_sub(t2, t2, v0); f2_sub(t2, t2, v2); f2_add(r.c2, t2, v1);
+    r.c0 = x0; r.c1 = x1;
+}
+// a * (b0 + b1 v)
+ZKV_HD ZKV_NOINLINE void f6_mul_01(fp6& r, const fp6& a, const fp2& b0, const fp2& b1) {
+    fp2 v0, v1, t0, t1, t2, x0, x2;
+    f2_mul(v0, a.c0, b0); f2_mul(v1, a.c1, b1);
+    f2_mul(t2, a.c2, b1); f2_mul_xi(t2, t2); f2_add(x0, t2, v0);          // c0 = a0 b0 + xi a2 b1
+    f2_mul(t2, a.c2, b0); f2_add(x2, t2, v1);                             // c2 = a1 b1 + a2 b0
+    f2_add(t0, a.c0, a.c1); f2_add(t1, b0, b1); f2_mul(t2, t0, t1);       // c1 = (a0+a1)(b0+b1) - v0 - v1
+    f2_sub(t2, t2, v0); f2_sub(r.c1, t2, v1);
+    r.c0 = x0; r.c2 = x2;
+}
+ZKV_HD ZKV_NOINLINE void f6_inv(fp6& r, const fp6& a) {
+    fp2 A, B, C, t, F;
+    f2_sqr(A, a.c0); f2_mul(t, a.c1, a.c2); f2_mul_xi(t, t); f2_sub(A, A, t);
+    f2_sqr(B, a.c2); f2_mul_xi(B, B); f2_mul(t, a.c0, a.c1); f2_sub(B, B, t);
+    f2_sqr(C, a.c1); f2_mul(t, a.c0, a.c2); f2_sub(C, C, t);
+    f2_mul(F, a.c0, A);
+    f2_mul(t, a.c2, B); f2_mul_xi(t, t); f2_add(F, F, t);
+    f2_mul(t, a.c1, C); f2_mul_xi(t, t); f2_add(F, F, t);
+    f2_inv(F, F);
+    f2_mul(r.c0, A, F); f2_mul(r.c1, B, F); f2_mul(r.c2, C, F);
+}
+
+// ------------------------------------------------------------------------------------------ Fp12 = Fp6[w]/(w^2 - v)
+ZKV_HD ZKV_INLINE fp12 f12_one() {
+    fp12 r; fp2 z = f2_zero();
+    r.c0.c0 = f2_one(); r.c0.c1 = z; r.c0.c2 = z; r.c1.c0 = z; r.c1.c1 = z; r.c1.c2 = z; return r;
+}
+ZKV_HD ZKV_INLINE bool f12_is_one(const fp12& a) {
+    fp one = fp_one(); const fp* w = &a.c0.c0.c0; uint32_t t = 0;
+    for (int i = 0; i < 8; i++) t |= w[0].v[i] ^ one.v[i];
+    for (int k = 1; k < 12; k++) for (int i = 0; i < 8; i++) t |= w[k].v[i];
+    return t == 0;
+}
+ZKV_HD ZKV_NOINLINE void f12_mul(fp12& r, const fp12& a, const fp12& b) {
+    fp6 t0, t1, s0, s1, m;
+    f6_mul(t0, a.c0, b.c0); f6_mul(t1, a.c1, b.c1);
+    f6_add(s0, a.c0, a.c1); f6_add(s1, b.c0, b.c1); f6_mul(m, s0, s1);
+    f6_sub(m, m, t0); f6_sub(r.c1, m, t1);
+    f6_mul_v(t1, t1); f6_add(r.c0, t0, t1);
+}
+// complex squaring: c0 = (a0+a1)(a0+v a1) - a0a1 - v a0a1 ; c1 = 2 a0a1
+ZKV_HD ZKV_NOINLINE void f12_sqr(fp12& r, const fp12& a) {
+    fp6 ab, s0, s1, t;
+    f6_mul(ab, a.c0, a.c1);
+    f6_add(s0, a.c0, a.c1); f6_mul_v(t, a.c1); f6_add(s1, a.c0, t);
+    f6_mul(s0, s0, s1);
+    f6_sub(s0, s0, ab); f6_mul_v(t, ab); f6_sub(r.c0, s0, t);
+    f6_add(r.c1, ab, ab);
+}
+ZKV_HD ZKV_INLINE void f12_conj(fp12& r, const fp12& a) { r.c0 = a.c0; f6_neg(r.c1, a.c1); }
+ZKV_HD ZKV_NOINLINE void f12_inv(fp12& r, const fp12& a) {
+    fp6 t0, t1;
+    f6_mul(t0, a.c0, a.c0); f6_mul(t1, a.c1, a.c1); f6_mul_v(t1, t1); f6_sub(t0, t0, t1);
+    f6_inv(t0, t0);
+    f6_mul(r.c0, a.c0, t0); f6_mul(t1, a.c1, t0); f6_neg(r.c1, t1);
+}
+// f *= l0 + (l3 + l4 v) w      (sparse "034" line product, 13 Fp2 multiplications)
+ZKV_HD ZKV_NOINLINE void f12_mul_line(fp12& f, const fp2& l0, const fp2& l3, const fp2& l4) {
+    fp6 t0, t1, s; fp2 l03;
+    f2_mul(t0.c0, f.c0.c0, l0); f2_mul(t0.c1, f.c0.c1, l0); f2_mul(t0.c2, f.c0.c2, l0);
+    f6_mul_01(t1, f.c1, l3, l4);
+    f6_add(s, f.c0, f.c1); f2_add(l03, l0, l3);
+    f6_mul_01(s, s, l03, l4);
+    f6_sub(s, s, t0); f6_sub(f.c1, s, t1);
+    f6_mul_v(t1, t1); f6_add(f.c0, t0, t1);
+}
+// f^(p^k), k in {1,2,3}
+ZKV_HD ZKV_NOINLINE void f12_frob(fp12& r, const fp12& a, int k) {
+    fp2 c[6] = {a.c0.c0, a.c1.c0, a.c0.c1, a.c1.c1, a.c0.c2, a.c1.c2};   // coefficient of w^i
+    for (int i = 0; i < 6; i++) {
+        if (k & 1) f2_conj(c[i], c[i]);
+        if (i) {
+            fp2 g = (k == 1) ? f2_const(C_FROB1[i]) : (k == 2) ? f2_const(C_FROB2[i]) : f2_const(C_FROB3[i]);
+            f2_mul(c[i], c[i], g);
+        }
+    }
+    r.c0.c0 = c[0]; r.c1.c0 = c[1]; r.c0.c1 = c[2]; r.c1.c1 = c[3]; r.c0.c2 = c[4]; r.c1.c2 = c[5];
+}
+// one Fp4 squaring (a + b s)^2, s^2 = xi: t0 = a^2 + xi b^2, t1 = 2ab
+ZKV_HD ZKV_INLINE void fp4_sqr(fp2& t0, fp2& t1, const fp2& a, const fp2& b) {
+    fp2 a2, b2, s;
+    f2_sqr(a2, a); f2_sqr(b2, b);
+    f2_add(s, a, b); f2_sqr(s, s); f2_sub(s, s, a2); f2_sub(t1, s, b2);
+    f2_mul_xi(b2, b2); f2_add(t0, a2, b2);
+}
+// Granger-Scott squaring; valid only for elements of the cyclotomic subgroup
+ZKV_HD ZKV_NOINLINE void f12_cyc_sqr(fp12& r, const fp12& a) {
+    fp2 t0, t1, t2, t3, t4, t5, x;
+    fp4_sqr(t0, t1, a.c0.c0, a.c1.c1);
+    fp4_sqr(t2, t3, a.c1.c0, a.c0.c2);
+    fp4_sqr(t4, t5, a.c0.c1, a.c1.c2);
+    fp2 z0 = a.c0.c0, z4 = a.c0.c1, z3 = a.c0.c2, z2 = a.c1.c0, z1 = a.c1.c1, z5 = a.c1.c2;
+    f2_sub(x, t0, z0); f2_dbl(x, x); f2_add(r.c0.c0, x, t0);     // 3 t0 - 2 z0
+    f2_add(x, t1, z1); f2_dbl(x, x); f2_add(r.c1.c1, x, t1);     // 3 t1 + 2 z1
+    f2_mul_xi(t5, t5);
+    f2_add(x, t5, z2); f2_dbl(x, x); f2_add(r.c1.c0, x, t5);     // 3 xi t5 + 2 z2
+    f2_sub(x, t4, z3); f2_dbl(x, x); f2_add(r.c0.c2, x, t4);     // 3 t4 - 2 z3
+    f2_sub(x, t2, z4); f2_dbl(x, x); f2_add(r.c0.c1, x, t2);     // 3 t2 - 2 z4
+    f2_add(x, t3, z5); f2_dbl(x, x); f2_add(r.c1.c2, x, t3);     // 3 t3 + 2 z5
+}
+ZKV_HD ZKV_NOINLINE void f12_pow_u(fp12& r, const fp12& a) {   // a^u, a in the cyclotomic subgroup
+    fp12 acc = a;
+    for (int i = 61; i >= 0; i--) {
+        f12_cyc_sqr(acc, acc);
+        if ((ZKV_BN_U >> i) & 1) f12_mul(acc, acc, a);
+    }
+    r = acc;
+}
+// GT = m^((p^6-1)(p^2+1)(L0 + L1 p + L2 p^2 + L3 p^3)), L_i as in DESIGN.md section 3 (same value as the oracle's final_exp)
+ZKV_HD ZKV_NOINLINE void final_exp(fp12& out, const fp12& m) {
+    fp12 f, t, t1;
+    f12_conj(t, m); f12_inv(t1, m); f12_mul(f, t, t1);
+    f12_frob(t, f, 2); f12_mul(f, t, f);
+    fp12 fu, f2u, f6u, f6u2, a, b;
+    f12_pow_u(fu, f);
+    f12_cyc_sqr(f2u, fu); f12_cyc_sqr(t, f2u); f12_mul(f6u, t, f2u);
+    f12_pow_u(f6u2, f6u); f12_cyc_sqr(t, f6u2); f12_pow_u(t1, t);      // t1 = f^(12u^3)
+    f12_mul(a, t1, f6u2); f12_mul(a, a, f6u);
+    f12_conj(t, f2u); f12_mul(b, a, t);
+    f12_mul(t1, a, f6u2); f12_mul(t1, t1, f);
+    f12_frob(t, b, 1); f12_mul(t1, t1, t);
+    f12_frob(t, a, 2); f12_mul(t1, t1, t);
+    f12_conj(t, f); f12_mul(t, b, t); f12_frob(t, t, 3);
+    f12_mul(out, t1, t);
+}
+
+// ------------------------------------------------------------------------------------------ G1: y^2 = x^3 + 3
+struct g1j { fp x, y, z; };            // Jacobian; z == 0 is infinity
+ZKV_HD ZKV_INLINE bool g1_on_curve(const fp& x, const fp& y) {
+    fp l, r, three = fp_const(C_THREE); fp_sqr(l, y); fp_sqr(r, x); fp_mul(r, r, x); fp_add(r, r, three); return fp_eq(l, r);
+}
+ZKV_HD ZKV_NOINLINE void g1_dbl(g1j& r, const g1j& p) {   // infinity-safe: z=0 stays z=0
+    fp A, B, C, D, E, F, t, x3, y3, z3;
+    fp_sqr(A, p.x); fp_sqr(B, p.y); fp_sqr(C, B);
+    fp_add(t, p.x, B); fp_sqr(t, t); fp_sub(t, t, A); fp_sub(t, t, C); fp_dbl(D, t);
+    fp_dbl(E, A); fp_add(E, E, A); fp_sqr(F, E);
+    fp_dbl(t, D); fp_sub(x3, F, t);
+    fp_sub(t, D, x3); fp_mul(y3, E, t); fp_dbl(t, C); fp_dbl(t, t); fp_dbl(t, t); fp_sub(y3, y3, t);
+    fp_mul(z3, p.y, p.z); fp_dbl(z3, z3);
+    r.x = x3; r.y = y3; r.z = z3;
+}
+// acc += (x2,y2) affine, complete (handles acc = inf, equal and opposite points)
+ZKV_HD ZKV_NOINLINE void g1_add_affine(g1j& acc, const fp& x2, const fp& y2) {
+    if (fp_is_zero(acc.z)) { acc.x = x2; acc.y = y2; acc.z = fp_one(); return; }
+    fp z1z1, u2, s2, h, rr, hh, hhh, v, t, x3, y3;
+    fp_sqr(z1z1, acc.z); fp_mul(u2, x2, z1z1); fp_mul(s2, y2, acc.z); fp_mul(s2, s2, z1z1);
+    fp_sub(h, u2, acc.x); fp_sub(rr, s2, acc.y);
+    if (fp_is_zero(h)) {
+        if (fp_is_zero(rr)) { g1j d; g1_dbl(d, acc); acc = d; }
+        else { acc.x = fp_one(); acc.y = fp_one(); acc.z = fp_zero(); }
+        return;
+    }
+    fp_sqr(hh, h); fp_mul(hhh, hh, h); fp_mul(v, acc.x, hh);
+    fp_sqr(x3, rr); fp_sub(x3, x3, hhh); fp_dbl(t, v); fp_sub(x3, x3, t);
+    fp_sub(t, v, x3); fp_mul(y3, rr, t); fp_mul(t, acc.y, hhh); fp_sub(y3, y3, t);
+    fp_mul(acc.z, acc.z, h); acc.x = x3; acc.y = y3;
+}
+ZKV_HD ZKV_INLINE bool g1_to_affine(fp& x, fp& y, const g1j& p) {   // returns false for infinity (x=y=0)
+    if (fp_is_zero(p.z)) { x = fp_zero(); y = fp_zero(); return false; }
+    fp zi, zi2; fp_inv(zi, p.z); fp_sqr(zi2, zi); fp_mul(x, p.x, zi2); fp_mul(zi2, zi2, zi); fp_mul(y, p.y, zi2); return true;
+}
+
+// ------------------------------------------------------------------------------------------ G2 on the twist y^2 = x^3 + 3/xi
+struct g2j { fp2 x, y, z; };           // Jacobian for the subgroup test; homogeneous projective in the Miller loop
+ZKV_HD ZKV_INLINE bool g2_on_curve(const fp2& x, const fp2& y) {
+    fp2 l, r, b = f2_const(C_TWIST_B); f2_sqr(l, y); f2_sqr(r, x); f2_mul(r, r, x); f2_add(r, r, b); return f2_eq(l, r);
+}
+ZKV_HD ZKV_NOINLINE void g2_dbl(g2j& r, const g2j& p) {
+    fp2 A, B, C, D, E, F, t, x3, y3, z3;
+    f2_sqr(A, p.x); f2_sqr(B, p.y); f2_sqr(C, B);
+    f2_add(t, p.x, B); f2_sqr(t, t); f2_sub(t, t, A); f2_sub(t, t, C); f2_dbl(D, t);
+    f2_dbl(E, A); f2_add(E, E, A); f2_sqr(F, E);
+    f2_dbl(t, D); f2_sub(x3, F, t);
+    f2_sub(t, D, x3); f2_mul(y3, E, t); f2_dbl(t, C); f2_dbl(t, t); f2_dbl(t, t); f2_sub(y3, y3, t);
+    f2_mul(z3, p.y, p.z); f2_dbl(z3, z3);
+    r.x = x3; r.y = y3; r.z = z3;
+}
+ZKV_HD ZKV_NOINLINE void g2_add(g2j& r, const g2j& p, const g2j& q) {   // complete
+    if (f2_is_zero(p.z)) { r = q; return; }
+    if (f2_is_zero(q.z)) { r = p; return; }
+    fp2 z1z1, z2z2, u1, u2, s1, s2, h, rr, t, hh, hhh, v, x3, y3, z3;
+    f2_sqr(z1z1, p.z); f2_sqr(z2z2, q.z);
+    f2_mul(u1, p.x, z2z2); f2_mul(u2, q.x, z1z1);
+    f2_mul(s1, p.y, q.z); f2_mul(s1, s1, z2z2);
+    f2_mul(s2, q.y, p.z); f2_mul(s2, s2, z1z1);
+    f2_sub(h, u2, u1); f2_sub(rr, s2, s1);
+    if (f2_is_zero(h)) {
+        if (f2_is_zero(rr)) { g2_dbl(r, p); }
+        else { r.x = f2_one(); r.y = f2_one(); r.z = f2_zero(); }
+        return;
+    }
+    f2_sqr(hh, h); f2_mul(hhh, hh, h); f2_mul(v, u1, hh);
+    f2_sqr(x3, rr); f2_sub(x3, x3, hhh); f2_dbl(t, v); f2_sub(x3, x3, t);
+    f2_sub(t, v, x3); f2_mul(y3, rr, t); f2_mul(t, s1, hhh); f2_sub(y3, y3, t);
+    f2_mul(z3, p.z, q.z); f2_mul(z3, z3, h);
+    r.x = x3; r.y = y3; r.z = z3;
+}
+// psi^k = twist o Frobenius^k o untwist, on Jacobian coordinates
+ZKV_HD ZKV_INLINE void g2_psi(g2j& r, const g2j& p, int k) {
+    fp2 x = p.x, y = p.y, z = p.z;
+    if (k & 1) { f2_conj(x, x); f2_conj(y, y); f2_conj(z, z); }
+    fp2 gx = (k == 1) ? f2_const(C_FROB1[2]) : (k == 2) ? f2_const(C_FROB2[2]) : f2_const(C_FROB3[2]);
+    fp2 gy = (k == 1) ? f2_const(C_FROB1[3]) : (k == 2) ? f2_const(C_FROB2[3]) : f2_const(C_FROB3[3]);
+    f2_mul(r.x, x, gx); f2_mul(r.y, y, gy); r.z = z;
+}
+ZKV_HD ZKV_INLINE bool g2j_eq(const g2j& a, const g2j& b) {
+    bool ia = f2_is_zero(a.z), ib = f2_is_zero(b.z);
+    if (ia || ib) return ia && ib;
+    fp2 za2, zb2, l, r; f2_sqr(za2, a.z); f2_sqr(zb2, b.z);
+    f2_mul(l, a.x, zb2); f2_mul(r, b.x, za2); if (!f2_eq(l, r)) return false;
+    f2_mul(za2, za2, a.z); f2_mul(zb2, zb2, b.z); f2_mul(l, a.y, zb2); f2_mul(r, b.y, za2); return f2_eq(l, r);
+}
+// Order-r membership for a point ON the twist: [u+1]Q + psi([u]Q) + psi^2([u]Q) == psi^3([2u]Q).
+// (BN-curve test of Dai-Lin-Zhao-Zhou, eprint 2022/348 sec. 3.1.)  Same accept set as the oracle's [r]Q == inf,
+// which is what tests/ check on subgroup, wrong-subgroup and small-order twist points.
+ZKV_HD ZKV_NOINLINE bool g2_in_subgroup(const fp2& qx, const fp2& qy) {
+    g2j q; q.x = qx; q.y = qy; q.z = f2_one();
+    g2j uq = q;
+    for (int i = 61; i >= 0; i--) {
+        g2j t; g2_dbl(t, uq); uq = t;
+        if ((ZKV_BN_U >> i) & 1) { g2_add(t, uq, q); uq = t; }
+    }
+    g2j lhs, t, p1, p2, p3;
+    g2_add(lhs, uq, q);
+    g2_psi(p1, uq, 1); g2_add(t, lhs, p1); lhs = t;
+    g2_psi(p2, uq, 2); g2_add(t, lhs, p2); lhs = t;
+    g2_dbl(t, uq); g2_psi(p3, t, 3);
+    return g2j_eq(lhs, p3);
+}
+
+// ------------------------------------------------------------------------------------------ Miller-loop steps
+// R in homogeneous projective coordinates (x = X/Z, y = Y/Z); a line is (l0,l3,l4) meaning
+// l0*yP + l3*xP*w + l4*v*w.  Formulas = oracle/bn254.h line_dbl/line_add (the shared convention).
+struct line_t { fp2 l0, l3, l4; };
+ZKV_HD ZKV_NOINLINE void line_dbl(g2j& R, line_t& l) {
+    fp2 A, B, C, E, F, G, H, J, E2, t, tb = f2_const(C_TWIST_B);
+    f2_mul(A, R.x, R.y); f2_half(A, A);
+    f2_sqr(B, R.y); f2_sqr(C, R.z);
+    f2_dbl(t, C); f2_add(t, t, C); f2_mul(E, tb, t);
+    f2_dbl(F, E); f2_add(F, F, E);
+    f2_add(G, B, F); f2_half(G, G);
+    f2_add(H, R.y, R.z); f2_sqr(H, H); f2_add(t, B, C); f2_sub(H, H, t);
+    f2_sub(l.l4, E, B);
+    f2_sqr(J, R.x);
+    f2_sqr(E2, E);
+    f2_sub(t, B, F); f2_mul(R.x, A, t);
+    f2_sqr(G, G); f2_dbl(t, E2); f2_add(t, t, E2); f2_sub(R.y, G, t);
+    f2_mul(R.z, B, H);
+    f2_neg(l.l0, H); f2_dbl(l.l3, J); f2_add(l.l3, l.l3, J);
+}
+ZKV_HD ZKV_NOINLINE void line_add(g2j& R, const fp2& qx, const fp2& qy, line_t& l) {
+    fp2 th, la, C, D, E, F, G, H, t, t2;
+    f2_mul(t, qy, R.z); f2_sub(th, R.y, t);
+    f2_mul(t, qx, R.z); f2_sub(la, R.x, t);
+    f2_sqr(C, th); f2_sqr(D, la); f2_mul(E, la, D); f2_mul(F, R.z, C); f2_mul(G, R.x, D);
+    f2_add(H, E, F); f2_dbl(t, G); f2_sub(H, H, t);
+    f2_mul(t, th, qx); f2_mul(t2, la, qy); f2_sub(l.l4, t, t2);
+    l.l0 = la; f2_neg(l.l3, th);
+    f2_sub(t, G, H); f2_mul(t, th, t); f2_mul(t2, E, R.y); f2_sub(R.y, t, t2);
+    f2_mul(R.x, la, H);
+    f2_mul(R.z, R.z, E);
+}
+ZKV_HD ZKV_INLINE void g2_frob_affine(fp2& x, fp2& y, int k) {   // pi^k on affine twist coordinates, k = 1, 2
+    if (k & 1) { f2_conj(x, x); f2_conj(y, y); }
+    fp2 gx = (k == 1) ? f2_const(C_FROB1[2]) : f2_const(C_FROB2[2]);
+    fp2 gy = (k == 1) ? f2_const(C_FROB1[3]) : f2_const(C_FROB2[3]);
+    f2_mul(x, x, gx); f2_mul(y, y, gy);
+}
+// f *= line evaluated at the G1 point (px, py)
+ZKV_HD ZKV_INLINE void f12_mul_line_at(fp12& f, const line_t& l, const fp& px, const fp& py) {
+    fp2 a, b; f2_mul_fp(a, l.l0, py); f2_mul_fp(b, l.l3, px);
+    f12_mul_line(f, a, b, l.l4);
+}
+// all ZKV_LINES_PER_G2 lines of a fixed G2 point, in the order the Miller loop consumes them
+ZKV_HD inline void g2_precompute_lines(line_t* out, const fp2& qx, const fp2& qy) {
+    g2j R; R.x = qx; R.y = qy; R.z = f2_one();
+    int n = 0;
+    for (int d = ZKV_ATE_NAF_LEN - 2; d >= 0; d--) {
+        line_dbl(R, out[n++]);
+        int dg = C_ATE_NAF[d];
+        if (dg) { fp2 y = qy; if (dg < 0) f2_neg(y, y); line_add(R, qx, y, out[n++]); }
+    }
+    fp2 x1 = qx, y1 = qy; g2_frob_affine(x1, y1, 1);
+    fp2 x2 = qx, y2 = qy; g2_frob_affine(x2, y2, 2); f2_neg(y2, y2);
+    line_add(R, x1, y1, out[n++]);
+    line_add(R, x2, y2, out[n++]);
+}
+
+// Multi-Miller loop: one variable G2 (qx,qy; pair 0) + nfixed tabled G2 points (pairs 1..nfixed).
+// skip bit j set => pair j contributes 1 (a member is infinity).  px/py: G1 points (Montgomery, affine).
+ZKV_HD inline void miller_loop(fp12& f, const fp* px, const fp* py, const fp2& qx, const fp2& qy,
+                               const line_t* const* tabs, int nfixed, uint32_t skip) {
+    f = f12_one();
+    g2j R; R.x = qx; R.y = qy; R.z = f2_one();
+    line_t l; int li = 0;
+    const bool var_on = !(skip & 1u);
+    for (int d = ZKV_ATE_NAF_LEN - 2; d >= 0; d--) {
+        if (d != ZKV_ATE_NAF_LEN - 2) f12_sqr(f, f);
+        if (var_on) { line_dbl(R, l); f12_mul_line_at(f, l, px[0], py[0]); }
+        for (int j = 0; j < nfixed; j++) if (!((skip >> (j + 1)) & 1u)) f12_mul_line_at(f, tabs[j][li], px[j + 1], py[j + 1]);
+        li++;
+        int dg = C_ATE_NAF[d];
+        if (dg) {
+            if (var_on) { fp2 y = qy; if (dg < 0) f2_neg(y, y); line_add(R, qx, y, l); f12_mul_line_at(f, l, px[0], py[0]); }
+            for (int j = 0; j < nfixed; j++) if (!((skip >> (j + 1)) & 1u)) f12_mul_line_at(f, tabs[j][li], px[j + 1], py[j + 1]);
+            li++;
+        }
+    }
+    fp2 x1 = qx, y1 = qy; g2_frob_affine(x1, y1, 1);
+    fp2 x2 = qx, y2 = qy; g2_frob_affine(x2, y2, 2); f2_neg(y2, y2);
+    for (int s = 0; s < 2; s++) {
+        if (var_on) { line_add(R, s ? x2 : x1, s ? y2 : y1, l); f12_mul_line_at(f, l, px[0], py[0]); }
+        for (int j = 0; j < nfixed; j++) if (!((skip >> (j + 1)) & 1u)) f12_mul_line_at(f, tabs[j][li], px[j + 1], py[j + 1]);
+        li++;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ byte <-> field
+ZKV_HD ZKV_INLINE void be32_to_raw(uint32_t* v, const uint8_t* b) {   // 32-byte big-endian -> 8 LE limbs (no reduction)
+    for (int i = 0; i < 8; i++) { const uint8_t* q = b + 4 * (7 - i); v[i] = (uint32_t)q[0] << 24 | (uint32_t)q[1] << 16 | (uint32_t)q[2] << 8 | q[3]; }
+}
+ZKV_HD ZKV_INLINE void raw_to_be32(uint8_t* b, const uint32_t* v) {
+    for (int i = 0; i < 8; i++) { uint8_t* q = b + 4 * (7 - i); q[0] = v[i] >> 24; q[1] = v[i] >> 16; q[2] = v[i] >> 8; q[3] = v[i]; }
+}
+ZKV_HD ZKV_INLINE void fp_to_be32(uint8_t* b, const fp& a) { fp t; fp_from_mont(t, a); raw_to_be32(b, t.v); }
+ZKV_HD inline void f12_to_bytes(uint8_t* out, const fp12& a) {   // 12 x BE-32, tower order c0.c0.c0, c0.c0.c1, c0.c1.c0, ...
+    const fp* w = &a.c0.c0.c0;
+    for (int i = 0; i < 12; i++) fp_to_be32(out + 32 * i, w[i]);
+}
+
+}  // namespace zkv

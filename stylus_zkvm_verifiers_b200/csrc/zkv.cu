@@ -1,0 +1,688 @@
+// libzkv_b200.so -- host side of the C ABI declared in include/zkv.h.
+//
+// Mirrors, batch-wise, the reference's verifier objects:
+//   zkv_vk      <- common/types.rs:17-23 VerificationKey (+ per-vk device tables built once on the GPU)
+//   zkv_risc0   <- risc0/verifier.rs:44-52 storage, :58-76 initialize, :78-104 verify / verify_integrity,
+//                  :128-144 calculate_selector, risc0/crypto.rs:136-195 compute_verifier_key_digest
+//   zkv_sp1     <- sp1/verifier.rs:31-54,58-111
+//   groth16     <- common/groth16.rs:23-128
+// Every verification entry point launches the sm_100a kernels of kernels.cuh; there is no CPU path.
+// Host work is limited to what the reference does before touching curve points: length / selector
+// checks (risc0/verifier.rs:151-170, sp1/verifier.rs:64-83), packing records into pinned staging,
+// and the once-per-handle SHA-256 bookkeeping of initialize().
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/zkv.h"
+#include "kernels.cuh"
+#include "vk_constants.h"
+
+using namespace zkv;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail(ZKV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" const char* zkv_last_error(void) { return g_err.c_str(); }
+extern "C" int zkv_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static constexpr int TPB = 128;                    // threads per block for the heavy kernels
+static constexpr size_t MAX_CHUNK = (size_t)1 << 20;   // proofs per device pass (workspace ~0.9 KB / proof)
+static inline int nblk(size_t n, int tpb = TPB) { return (int)((n + tpb - 1) / tpb); }
+
+// ------------------------------------------------------------------------------------------ host SHA helpers
+static void sha_bytes(uint8_t out[32], const uint8_t* msg, size_t len) { uint32_t h[8]; sha256_msg(h, msg, len); sha256_words_to_bytes(out, h); }
+static void sha_str(uint8_t out[32], const char* s) { sha_bytes(out, (const uint8_t*)s, strlen(s)); }
+static void bytes_to_words(uint32_t w[8], const uint8_t b[32]) { for (int k = 0; k < 8; k++) w[k] = load_be32(b + 4 * k); }
+static const uint8_t FR_R_BE[32] = {0x30, 0x64, 0x4e, 0x72, 0xe1, 0x31, 0xa0, 0x29, 0xb8, 0x50, 0x45, 0xb6, 0x81, 0x81, 0x58, 0x5d,
+                                    0x28, 0x33, 0xe8, 0x48, 0x79, 0xb9, 0x70, 0x91, 0x43, 0xe1, 0xf5, 0x93, 0xf0, 0x00, 0x00, 0x01};   // R, groth16.rs:9
+
+// ------------------------------------------------------------------------------------------ per-device context
+struct DevCtx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // per-vk tables (device memory, Montgomery form)
+    VkDev* d_vk = nullptr; line_t* d_lines = nullptr; fp12* d_pre = nullptr; g1aff* d_tab = nullptr; g1aff* d_ic0 = nullptr;
+    VkDev h_vk; g1aff h_ic0;
+    // workspace
+    size_t cap = 0;
+    fp* px[4] = {nullptr, nullptr, nullptr, nullptr}; fp* py[4] = {nullptr, nullptr, nullptr, nullptr};
+    fp2 *qx = nullptr, *qy = nullptr; fp12* f = nullptr; uint8_t *flags = nullptr, *status = nullptr; uint32_t* scal = nullptr; size_t scal_words = 0;
+    // staging
+    uint8_t* d_in = nullptr; size_t d_in_cap = 0; uint8_t* d_out = nullptr; size_t d_out_cap = 0;
+    uint8_t* h_pin = nullptr; size_t h_pin_cap = 0; uint8_t* h_out = nullptr; size_t h_out_cap = 0;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float stage_ms[5] = {0, 0, 0, 0, 0};
+    std::mutex mu;
+};
+
+static int ctx_reserve(DevCtx* c, size_t n, size_t scal_words_per_proof) {
+    if (n > c->cap) {
+        for (int j = 0; j < 4; j++) { cudaFree(c->px[j]); cudaFree(c->py[j]); }
+        cudaFree(c->qx); cudaFree(c->qy); cudaFree(c->f); cudaFree(c->flags); cudaFree(c->status);
+        c->cap = 0;
+        for (int j = 0; j < 4; j++) { CK(cudaMalloc(&c->px[j], n * sizeof(fp))); CK(cudaMalloc(&c->py[j], n * sizeof(fp))); }
+        CK(cudaMalloc(&c->qx, n * sizeof(fp2))); CK(cudaMalloc(&c->qy, n * sizeof(fp2))); CK(cudaMalloc(&c->f, n * sizeof(fp12)));
+        CK(cudaMalloc(&c->flags, n)); CK(cudaMalloc(&c->status, n));
+        c->cap = n;
+    }
+    size_t need = n * scal_words_per_proof;
+    if (need > c->scal_words) { cudaFree(c->scal); c->scal_words = 0; CK(cudaMalloc(&c->scal, need * 4)); c->scal_words = need; }
+    return 0;
+}
+static int ctx_stage(DevCtx* c, size_t in_bytes, size_t out_bytes) {
+    if (in_bytes > c->d_in_cap) { cudaFree(c->d_in); cudaFreeHost(c->h_pin); c->d_in_cap = 0; c->h_pin_cap = 0;
+        size_t cap = in_bytes + in_bytes / 4 + 4096; CK(cudaMalloc(&c->d_in, cap)); CK(cudaMallocHost(&c->h_pin, cap)); c->d_in_cap = cap; c->h_pin_cap = cap; }
+    if (out_bytes > c->d_out_cap) { cudaFree(c->d_out); cudaFreeHost(c->h_out); c->d_out_cap = 0; c->h_out_cap = 0;
+        size_t cap = out_bytes + out_bytes / 4 + 4096; CK(cudaMalloc(&c->d_out, cap)); CK(cudaMallocHost(&c->h_out, cap)); c->d_out_cap = cap; c->h_out_cap = cap; }
+    return 0;
+}
+static void ctx_free(DevCtx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (int j = 0; j < 4; j++) { cudaFree(c->px[j]); cudaFree(c->py[j]); }
+    cudaFree(c->qx); cudaFree(c->qy); cudaFree(c->f); cudaFree(c->flags); cudaFree(c->status); cudaFree(c->scal);
+    cudaFree(c->d_in); cudaFree(c->d_out); cudaFreeHost(c->h_pin); cudaFreeHost(c->h_out);
+    cudaFree(c->d_vk); cudaFree(c->d_lines); cudaFree(c->d_pre); cudaFree(c->d_tab); cudaFree(c->d_ic0);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// ------------------------------------------------------------------------------------------ verification key
+struct zkv_vk {
+    int vm = 0, n_ic = 0;
+    uint8_t alpha[64], beta[128], gamma[128], delta[128];
+    std::vector<uint8_t> ic;
+    std::vector<DevCtx*> devs;
+    int valid = 1;     // every key point decodes under EIP-196/197 (else each verification's precompile call reverts -> false)
+};
+static DevCtx* vk_ctx(const zkv_vk* vk, int device) { for (auto* c : vk->devs) if (c->device == device) return c; return nullptr; }
+
+static int vk_build_on(zkv_vk* vk, DevCtx* c) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto& e : c->ev) CK(cudaEventCreate(&e));
+    int nt = vk->n_ic - 1;
+    CK(cudaMalloc(&c->d_vk, sizeof(VkDev))); CK(cudaMalloc(&c->d_lines, sizeof(line_t) * 3 * ZKV_LINES_PER_G2)); CK(cudaMalloc(&c->d_pre, sizeof(fp12)));
+    CK(cudaMalloc(&c->d_tab, sizeof(g1aff) * (size_t)nt * ZKV_WIN_PER_SCALAR * ZKV_WIN_ENTRIES)); CK(cudaMalloc(&c->d_ic0, sizeof(g1aff)));
+    uint8_t* d_bytes; size_t nb = 64 + 384 + vk->ic.size();
+    CK(cudaMalloc(&d_bytes, nb));
+    std::vector<uint8_t> hb(nb);
+    memcpy(hb.data(), vk->alpha, 64); memcpy(hb.data() + 64, vk->beta, 128); memcpy(hb.data() + 192, vk->gamma, 128); memcpy(hb.data() + 320, vk->delta, 128);
+    memcpy(hb.data() + 448, vk->ic.data(), vk->ic.size());
+    CK(cudaMemcpyAsync(d_bytes, hb.data(), nb, cudaMemcpyHostToDevice, c->stream));
+    VkDev init; memset(&init, 0, sizeof init); init.valid = 1;
+    CK(cudaMemcpyAsync(c->d_vk, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->d_lines, 0, sizeof(line_t) * 3 * ZKV_LINES_PER_G2, c->stream));
+    k_vk_setup<<<1, 4, 0, c->stream>>>(d_bytes, d_bytes + 64, c->d_vk, c->d_lines);
+    k_ic_tables<<<nt, ZKV_WIN_PER_SCALAR, 0, c->stream>>>(d_bytes + 448, c->d_tab, c->d_ic0, c->d_vk);
+    k_vk_miller_ab<<<1, 1, 0, c->stream>>>(c->d_vk, c->d_lines, c->d_pre);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&c->h_vk, c->d_vk, sizeof(VkDev), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&c->h_ic0, c->d_ic0, sizeof(g1aff), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaFree(d_bytes));
+    if (!c->h_vk.valid) vk->valid = 0;
+    return 0;
+}
+
+extern "C" void zkv_vk_free(zkv_vk* vk) {
+    if (!vk) return;
+    for (auto* c : vk->devs) ctx_free(c);
+    delete vk;
+}
+extern "C" int zkv_vk_load(int vm_type, const uint8_t alpha[64], const uint8_t beta[128], const uint8_t gamma[128], const uint8_t delta[128],
+                           const uint8_t* ic, int n_ic, const int* devices, int n_dev, zkv_vk** out) {
+    if (!out || !alpha || !beta || !gamma || !delta || !ic) return fail(ZKV_ERR_ARG, "zkv_vk_load: null argument");
+    if (vm_type != ZKV_VM_RISC0 && vm_type != ZKV_VM_SP1) return fail(ZKV_ERR_ARG, "zkv_vk_load: vm_type");
+    if (n_ic < 2 || n_ic > 16) return fail(ZKV_ERR_ARG, "zkv_vk_load: n_ic must be 2..16");
+    int ndev_sys = zkv_device_count();
+    if (ndev_sys <= 0) return fail(ZKV_ERR_CUDA, "zkv_vk_load: no CUDA device (this library has no CPU path)");
+    std::vector<int> devs;
+    if (!devices || n_dev <= 0) devs.push_back(0); else devs.assign(devices, devices + n_dev);
+    for (int d : devs) if (d < 0 || d >= ndev_sys) return fail(ZKV_ERR_ARG, "zkv_vk_load: bad device index");
+    zkv_vk* vk = new zkv_vk();
+    vk->vm = vm_type; vk->n_ic = n_ic;
+    memcpy(vk->alpha, alpha, 64); memcpy(vk->beta, beta, 128); memcpy(vk->gamma, gamma, 128); memcpy(vk->delta, delta, 128);
+    vk->ic.assign(ic, ic + 64 * (size_t)n_ic);
+    for (int d : devs) {
+        DevCtx* c = new DevCtx(); c->device = d; vk->devs.push_back(c);
+        int rc = vk_build_on(vk, c);
+        if (rc) { zkv_vk_free(vk); return rc; }
+    }
+    *out = vk;
+    return 0;
+}
+extern "C" int zkv_vk_load_risc0(const int* devices, int n_dev, zkv_vk** out) {
+    const uint8_t* p = ZKV_RISC0_VK_AB_GD;
+    return zkv_vk_load(ZKV_VM_RISC0, p, p + 64, p + 192, p + 320, ZKV_RISC0_VK_IC, 6, devices, n_dev, out);
+}
+extern "C" int zkv_vk_load_sp1(const int* devices, int n_dev, zkv_vk** out) {
+    const uint8_t* p = ZKV_SP1_VK_AB_GD;
+    return zkv_vk_load(ZKV_VM_SP1, p, p + 64, p + 192, p + 320, ZKV_SP1_VK_IC, 3, devices, n_dev, out);
+}
+
+// ------------------------------------------------------------------------------------------ the device pipeline
+enum SigMode { SIG_GENERIC, SIG_RISC0_VERIFY, SIG_RISC0_INTEGRITY, SIG_SP1 };
+struct Job {
+    const zkv_vk* vk; size_t n;
+    // proof records (device): rec i at recs + i*stride, 8 x BE-32 at +off; selector (if any) in the first 4 bytes
+    const uint8_t* recs; size_t stride, off; int check_selector; uint32_t selector_le;
+    SigMode mode;
+    const uint8_t *sig_a, *sig_b;           // generic: signals | risc0: image_ids, journals (or claims) | sp1: vkeys, public values
+    const uint64_t* pv_off; size_t pv_stride; int k;
+    Risc0HashConsts hc; g1aff base; int all_fail;
+    uint8_t* d_status;
+};
+__global__ void k_status_all_fail(int n, const uint8_t* flags, uint8_t* status) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) status[i] = (flags[i] & F_SELMIS) ? ST_SELECTOR_MISMATCH : ST_VERIFICATION_FAILED;
+}
+// enqueue all stages of one batch on c->stream (asynchronous); caller holds c->mu and has set the device
+static int run_verify(DevCtx* c, const Job& j) {
+    const zkv_vk* vk = j.vk; int n = (int)j.n;
+    if (n == 0) return 0;
+    int ns = (j.mode == SIG_GENERIC) ? j.k : 2;
+    int rc = ctx_reserve(c, j.n, (size_t)ns * 8); if (rc) return rc;
+    cudaStream_t s = c->stream;
+    CK(cudaEventRecord(c->ev[0], s));
+    k_decode<<<nblk(n), TPB, 0, s>>>(n, j.recs, j.stride, j.off, j.selector_le, j.check_selector, vk->vm, c->px[0], c->py[0], c->qx, c->qy, c->px[3], c->py[3], c->flags);
+    const g1aff* tab = c->d_tab; int nwin = ZKV_WIN_PER_SCALAR;
+    switch (j.mode) {
+        case SIG_GENERIC: k_generic_signals<<<nblk(n), TPB, 0, s>>>(n, j.k, j.sig_a, c->scal, c->flags); break;
+        case SIG_RISC0_VERIFY: k_risc0_signals<<<nblk(n), TPB, 0, s>>>(n, j.sig_a, j.sig_b, nullptr, 0, j.hc, c->scal); break;
+        case SIG_RISC0_INTEGRITY: k_risc0_signals<<<nblk(n), TPB, 0, s>>>(n, nullptr, nullptr, j.sig_a, 1, j.hc, c->scal); break;
+        case SIG_SP1: k_sp1_signals<<<nblk(n), TPB, 0, s>>>(n, j.sig_a, j.sig_b, j.pv_off, j.pv_stride, c->scal, c->flags); break;
+    }
+    if (j.mode == SIG_RISC0_VERIFY || j.mode == SIG_RISC0_INTEGRITY) { tab = c->d_tab + (size_t)2 * ZKV_WIN_PER_SCALAR * ZKV_WIN_ENTRIES; nwin = 32; }   // claim_lo / claim_hi are 128-bit
+    CK(cudaEventRecord(c->ev[1], s));
+    if (j.all_fail || !vk->valid) {
+        k_status_all_fail<<<nblk(n), TPB, 0, s>>>(n, c->flags, j.d_status);
+        for (int e = 2; e < 6; e++) CK(cudaEventRecord(c->ev[e], s));
+        CK(cudaGetLastError());
+        return 0;
+    }
+    k_vkx<<<nblk(n), TPB, 0, s>>>(n, c->scal, ns, nwin, tab, j.base, c->px[2], c->py[2], c->flags);
+    CK(cudaEventRecord(c->ev[2], s));
+    k_g2_check<<<nblk(n), TPB, 0, s>>>(n, c->qx, c->qy, c->flags);
+    CK(cudaEventRecord(c->ev[3], s));
+    MillerArgs a; memset(&a, 0, sizeof a);
+    a.px[0] = c->px[0]; a.py[0] = c->py[0]; a.px[1] = c->px[2]; a.py[1] = c->py[2]; a.px[2] = c->px[3]; a.py[2] = c->py[3];
+    a.qx = c->qx; a.qy = c->qy;
+    a.tabs[0] = c->d_lines + 1 * ZKV_LINES_PER_G2; a.tabs[1] = c->d_lines + 2 * ZKV_LINES_PER_G2;
+    a.nfixed = 2; a.pre = c->d_pre;
+    a.skip_bit[0] = F_SKIP0; a.skip_bit[1] = F_SKIPX; a.skip_bit[2] = F_SKIPC;
+    a.vk_skip = (uint8_t)((c->h_vk.g2_inf[1] ? 2 : 0) | (c->h_vk.g2_inf[2] ? 4 : 0));
+    k_miller<<<nblk(n), TPB, 0, s>>>(n, a, c->flags, c->f);
+    CK(cudaEventRecord(c->ev[4], s));
+    k_final_exp<<<nblk(n), TPB, 0, s>>>(n, c->f, c->flags, j.d_status, nullptr, 0);
+    CK(cudaEventRecord(c->ev[5], s));
+    CK(cudaGetLastError());
+    return 0;
+}
+static void collect_stage_ms(DevCtx* c) {
+    for (int e = 0; e < 5; e++) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[e], c->ev[e + 1]) != cudaSuccess) { cudaGetLastError(); ms = 0; } c->stage_ms[e] = ms; }
+}
+
+// Split `n` items over the vk's devices in contiguous ranges and run fn(ctx, begin, end) on one host thread per device.
+template <class F>
+static int for_each_device(const zkv_vk* vk, size_t n, F fn) {
+    size_t nd = vk->devs.size();
+    if (nd == 1 || n < 4096) {
+        DevCtx* c = vk->devs[0];
+        std::lock_guard<std::mutex> lk(c->mu);
+        CK(cudaSetDevice(c->device));
+        return fn(c, (size_t)0, n);
+    }
+    std::vector<int> rcs(nd, 0); std::vector<std::string> errs(nd);
+    std::vector<std::thread> th;
+    for (size_t d = 0; d < nd; d++) {
+        size_t b = n * d / nd, e = n * (d + 1) / nd;
+        th.emplace_back([&, d, b, e]() {
+            DevCtx* c = vk->devs[d];
+            std::lock_guard<std::mutex> lk(c->mu);
+            if (cudaSetDevice(c->device) != cudaSuccess) { rcs[d] = ZKV_ERR_CUDA; errs[d] = "cudaSetDevice"; return; }
+            rcs[d] = fn(c, b, e);
+            if (rcs[d]) errs[d] = g_err;
+        });
+    }
+    for (auto& t : th) t.join();
+    for (size_t d = 0; d < nd; d++) if (rcs[d]) return fail(rcs[d], errs[d]);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ generic Groth16
+extern "C" int zkv_groth16_verify_batch(const zkv_vk* vk, const uint8_t* proofs, const uint8_t* signals, int k, size_t n, uint8_t* status_out) {
+    if (!vk || (n && (!proofs || !status_out)) || k < 0 || (n && k && !signals)) return fail(ZKV_ERR_ARG, "zkv_groth16_verify_batch: bad argument");
+    if (n == 0) return 0;
+    if (k + 1 != vk->n_ic) { memset(status_out, ZKV_VERIFICATION_FAILED, n); return 0; }        // groth16.rs:32
+    return for_each_device(vk, n, [&](DevCtx* c, size_t b, size_t e) -> int {
+        for (size_t s0 = b; s0 < e; s0 += MAX_CHUNK) {
+            size_t m = std::min(MAX_CHUNK, e - s0);
+            size_t pb = m * 256, sb = m * (size_t)k * 32;
+            int rc = ctx_stage(c, pb + sb, m); if (rc) return rc;
+            memcpy(c->h_pin, proofs + s0 * 256, pb); memcpy(c->h_pin + pb, signals + s0 * (size_t)k * 32, sb);
+            CK(cudaMemcpyAsync(c->d_in, c->h_pin, pb + sb, cudaMemcpyHostToDevice, c->stream));
+            Job j; memset(&j, 0, sizeof j);
+            j.vk = vk; j.n = m; j.recs = c->d_in; j.stride = 256; j.off = 0; j.mode = SIG_GENERIC; j.sig_a = c->d_in + pb; j.k = k; j.base = c->h_ic0; j.d_status = c->d_out;
+            rc = run_verify(c, j); if (rc) return rc;
+            CK(cudaMemcpyAsync(c->h_out, c->d_out, m, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            collect_stage_ms(c);
+            memcpy(status_out + s0, c->h_out, m);
+        }
+        return 0;
+    });
+}
+
+// ------------------------------------------------------------------------------------------ RISC Zero
+struct zkv_risc0 {
+    const zkv_vk* vk = nullptr; zkv_vk* owned = nullptr;
+    int initialized = 0;
+    uint8_t control_root_0[16], control_root_1[16], bn254_control_id[32], selector[4], vk_digest[32];
+    Risc0HashConsts hc; g1aff base; int all_fail = 0;
+};
+// risc0/crypto.rs:136-195 compute_verifier_key_digest (over this handle's key)
+static void risc0_vk_digest(uint8_t out[32], const zkv_vk* vk) {
+    uint8_t ic_tag[32], vk_tag[32], cur[32], buf[32 * 7 + 2];
+    sha_str(ic_tag, "risc0_groth16.VerifyingKey.IC"); sha_str(vk_tag, "risc0_groth16.VerifyingKey");
+    memset(cur, 0, 32);
+    for (int i = vk->n_ic - 1; i >= 0; i--) {        // tagged_list -> tagged_list_cons, :124-134
+        memcpy(buf, ic_tag, 32); sha_bytes(buf + 32, vk->ic.data() + 64 * i, 64); memcpy(buf + 64, cur, 32); buf[96] = 0x02; buf[97] = 0x00;
+        sha_bytes(cur, buf, 98);
+    }
+    memcpy(buf, vk_tag, 32); sha_bytes(buf + 32, vk->alpha, 64); sha_bytes(buf + 64, vk->beta, 128); sha_bytes(buf + 96, vk->gamma, 128); sha_bytes(buf + 128, vk->delta, 128);
+    memcpy(buf + 160, cur, 32); buf[192] = 0x05; buf[193] = 0x00;    // tagged_struct: 5 down-digests, :112-122
+    sha_bytes(out, buf, 194);
+}
+extern "C" int zkv_risc0_create(const zkv_vk* vk_or_null, const int* devices, int n_dev, zkv_risc0** out) {
+    if (!out) return fail(ZKV_ERR_ARG, "zkv_risc0_create: null out");
+    zkv_risc0* h = new zkv_risc0();
+    if (vk_or_null) { if (vk_or_null->n_ic != 6 || vk_or_null->vm != ZKV_VM_RISC0) { delete h; return fail(ZKV_ERR_ARG, "zkv_risc0_create: need a ZKV_VM_RISC0 key with 6 IC points"); } h->vk = vk_or_null; }
+    else { int rc = zkv_vk_load_risc0(devices, n_dev, &h->owned); if (rc) { delete h; return rc; } h->vk = h->owned; }
+    *out = h; return 0;
+}
+extern "C" void zkv_risc0_destroy(zkv_risc0* h) { if (!h) return; if (h->owned) zkv_vk_free(h->owned); delete h; }
+
+extern "C" int zkv_risc0_initialize(zkv_risc0* h, const uint8_t control_root[32], const uint8_t bn254_control_id[32]) {
+    if (!h || !control_root || !bn254_control_id) return fail(ZKV_ERR_ARG, "zkv_risc0_initialize: null argument");
+    if (h->initialized) return fail(ZKV_ERR_STATE, "AlreadyInitialized");                     // risc0/verifier.rs:59-61
+    // split_digest(control_root), risc0/crypto.rs:103-110: reverse the 32 bytes, low = rev[16..], high = rev[..16]
+    uint8_t rev[32]; for (int i = 0; i < 32; i++) rev[i] = control_root[31 - i];
+    memcpy(h->control_root_0, rev + 16, 16); memcpy(h->control_root_1, rev, 16);
+    memcpy(h->bn254_control_id, bn254_control_id, 32);
+    // calculate_selector, risc0/verifier.rs:128-144
+    uint8_t buf[130], d[32];
+    sha_str(buf, "risc0.Groth16ReceiptVerifierParameters"); memcpy(buf + 32, control_root, 32);
+    for (int i = 0; i < 32; i++) buf[64 + i] = bn254_control_id[31 - i];
+    risc0_vk_digest(h->vk_digest, h->vk); memcpy(buf + 96, h->vk_digest, 32); buf[128] = 0x03; buf[129] = 0x00;
+    sha_bytes(d, buf, 130); memcpy(h->selector, d, 4);
+    // per-proof hashing constants (risc0/types.rs:62-95, config.rs:5-32)
+    uint8_t tag[32]; sha_str(tag, "risc0.Output"); bytes_to_words(h->hc.tag_out, tag);
+    sha_str(tag, "risc0.ReceiptClaim");
+    { uint32_t st[8], w[16]; sha256_init(st); bytes_to_words(w, tag); for (int k = 8; k < 16; k++) w[k] = 0; sha256_compress(st, w); memcpy(h->hc.claim_mid, st, 32); }
+    bytes_to_words(h->hc.sys0, ZKV_RISC0_SYSTEM_STATE_ZERO_DIGEST);
+    // signals 0,1,4 are instance constants (verifier.rs:172-179): fold them into the vk_x base point K = IC0 + s0 IC1 + s1 IC2 + s4 IC5
+    h->all_fail = memcmp(bn254_control_id, FR_R_BE, 32) >= 0;                                  // groth16.rs:32-34: signal >= R
+    DevCtx* c = h->vk->devs[0];
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        CK(cudaSetDevice(c->device));
+        int rc = ctx_reserve(c, 1, 24); if (rc) return rc;
+        uint32_t sc[24]; memset(sc, 0, sizeof sc);
+        uint8_t w32[32];
+        memset(w32, 0, 32); memcpy(w32 + 16, h->control_root_0, 16); for (int k = 0; k < 8; k++) sc[k] = load_be32(w32 + 4 * (7 - k));
+        memset(w32, 0, 32); memcpy(w32 + 16, h->control_root_1, 16); for (int k = 0; k < 8; k++) sc[8 + k] = load_be32(w32 + 4 * (7 - k));
+        for (int k = 0; k < 8; k++) sc[16 + k] = load_be32(bn254_control_id + 4 * (7 - k));
+        CK(cudaMemcpyAsync(c->scal, sc, sizeof sc, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(c->flags, 0, 1, c->stream));
+        if (!h->all_fail && h->vk->valid) {
+            k_vkx<<<1, 1, 0, c->stream>>>(1, c->scal, 2, ZKV_WIN_PER_SCALAR, c->d_tab, c->h_ic0, c->px[2], c->py[2], c->flags);
+            g1aff mid;
+            CK(cudaMemcpyAsync(&mid.x, c->px[2], sizeof(fp), cudaMemcpyDeviceToHost, c->stream)); CK(cudaMemcpyAsync(&mid.y, c->py[2], sizeof(fp), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            k_vkx<<<1, 1, 0, c->stream>>>(1, c->scal + 16, 1, ZKV_WIN_PER_SCALAR, c->d_tab + (size_t)4 * ZKV_WIN_PER_SCALAR * ZKV_WIN_ENTRIES, mid, c->px[2], c->py[2], c->flags);
+            CK(cudaMemcpyAsync(&h->base.x, c->px[2], sizeof(fp), cudaMemcpyDeviceToHost, c->stream)); CK(cudaMemcpyAsync(&h->base.y, c->py[2], sizeof(fp), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            CK(cudaGetLastError());
+        } else memset(&h->base, 0, sizeof h->base);
+    }
+    h->initialized = 1;
+    return 0;
+}
+extern "C" int zkv_risc0_is_initialized(const zkv_risc0* h) { return h ? h->initialized : 0; }
+extern "C" int zkv_risc0_get_selector(const zkv_risc0* h, uint8_t out[4]) { if (!h || !out) return fail(ZKV_ERR_ARG, "null"); if (h->initialized) memcpy(out, h->selector, 4); else memset(out, 0, 4); return 0; }
+extern "C" int zkv_risc0_get_control_root(const zkv_risc0* h, uint8_t out0[16], uint8_t out1[16]) {
+    if (!h || !out0 || !out1) return fail(ZKV_ERR_ARG, "null");
+    if (h->initialized) { memcpy(out0, h->control_root_0, 16); memcpy(out1, h->control_root_1, 16); } else { memset(out0, 0, 16); memset(out1, 0, 16); }
+    return 0;
+}
+extern "C" int zkv_risc0_get_bn254_control_id(const zkv_risc0* h, uint8_t out[32]) { if (!h || !out) return fail(ZKV_ERR_ARG, "null"); if (h->initialized) memcpy(out, h->bn254_control_id, 32); else memset(out, 0, 32); return 0; }
+extern "C" int zkv_risc0_get_verifier_key_digest(const zkv_risc0* h, uint8_t out[32]) { if (!h || !out) return fail(ZKV_ERR_ARG, "null"); risc0_vk_digest(out, h->vk); return 0; }
+
+// Host-side front checks shared by RISC Zero and SP1 (risc0/verifier.rs:151-170, sp1/verifier.rs:64-83):
+// returns the indices that reach the Groth16 stage; everything else gets its final status here.
+static void front_filter(const uint8_t* blobs, const uint64_t* off, size_t n, const uint8_t selector[4], uint8_t* status_out, std::vector<uint32_t>& cand) {
+    cand.clear(); cand.reserve(n);
+    for (size_t i = 0; i < n; i++) {
+        uint64_t len = off[i + 1] - off[i]; const uint8_t* p = blobs + off[i];
+        if (len < 4) { status_out[i] = ZKV_INVALID_PROOF_DATA; continue; }
+        if (memcmp(p, selector, 4) != 0) { status_out[i] = ZKV_SELECTOR_MISMATCH; continue; }
+        if (len - 4 != 256) { status_out[i] = ZKV_INVALID_PROOF_DATA; continue; }        // strict abi_decode of 8 x uint256
+        cand.push_back((uint32_t)i);
+    }
+}
+
+static int risc0_batch(const zkv_risc0* h, const uint8_t* seals, const uint64_t* seal_off, const uint8_t* a32, const uint8_t* b32, int integrity, size_t n, uint8_t* status_out) {
+    if (!h || (n && (!seals || !seal_off || !a32 || (!integrity && !b32) || !status_out))) return fail(ZKV_ERR_ARG, "zkv_risc0_verify_batch: null argument");
+    if (n == 0) return 0;
+    if (n > 0xffffffffull) return fail(ZKV_ERR_ARG, "batch too large");
+    if (!h->initialized) { memset(status_out, ZKV_INVALID_INITIALIZATION, n); return 0; }     // risc0/verifier.rs:84-86, 99-101
+    std::vector<uint32_t> cand; front_filter(seals, seal_off, n, h->selector, status_out, cand);
+    const zkv_vk* vk = h->vk;
+    return for_each_device(vk, cand.size(), [&](DevCtx* c, size_t b, size_t e) -> int {
+        for (size_t s0 = b; s0 < e; s0 += MAX_CHUNK) {
+            size_t m = std::min(MAX_CHUNK, e - s0);
+            size_t rb = m * 256, per = integrity ? 32 : 64;
+            int rc = ctx_stage(c, rb + m * per, m); if (rc) return rc;
+            uint8_t* pr = c->h_pin; uint8_t* pa = c->h_pin + rb; uint8_t* pb = pa + m * 32;
+            for (size_t t = 0; t < m; t++) {
+                size_t i = cand[s0 + t];
+                memcpy(pr + t * 256, seals + seal_off[i] + 4, 256); memcpy(pa + t * 32, a32 + i * 32, 32);
+                if (!integrity) memcpy(pb + t * 32, b32 + i * 32, 32);
+            }
+            CK(cudaMemcpyAsync(c->d_in, c->h_pin, rb + m * per, cudaMemcpyHostToDevice, c->stream));
+            Job j; memset(&j, 0, sizeof j);
+            j.vk = vk; j.n = m; j.recs = c->d_in; j.stride = 256; j.off = 0; j.mode = integrity ? SIG_RISC0_INTEGRITY : SIG_RISC0_VERIFY;
+            j.sig_a = c->d_in + rb; j.sig_b = c->d_in + rb + m * 32; j.hc = h->hc; j.base = h->base; j.all_fail = h->all_fail; j.d_status = c->d_out;
+            rc = run_verify(c, j); if (rc) return rc;
+            CK(cudaMemcpyAsync(c->h_out, c->d_out, m, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            collect_stage_ms(c);
+            for (size_t t = 0; t < m; t++) status_out[cand[s0 + t]] = c->h_out[t];
+        }
+        return 0;
+    });
+}
+extern "C" int zkv_risc0_verify_batch(const zkv_risc0* h, const uint8_t* seals, const uint64_t* seal_off, const uint8_t* image_ids, const uint8_t* journal_digests, size_t n, uint8_t* status_out) {
+    return risc0_batch(h, seals, seal_off, image_ids, journal_digests, 0, n, status_out);
+}
+extern "C" int zkv_risc0_verify_integrity_batch(const zkv_risc0* h, const uint8_t* seals, const uint64_t* seal_off, const uint8_t* claim_digests, size_t n, uint8_t* status_out) {
+    return risc0_batch(h, seals, seal_off, claim_digests, nullptr, 1, n, status_out);
+}
+extern "C" int zkv_risc0_verify(const zkv_risc0* h, const uint8_t* seal, size_t seal_len, const uint8_t image_id[32], const uint8_t journal_digest[32], uint8_t* status_out) {
+    uint64_t off[2] = {0, seal_len}; uint8_t dummy = 0;
+    return risc0_batch(h, seal ? seal : &dummy, off, image_id, journal_digest, 0, 1, status_out);
+}
+extern "C" int zkv_risc0_verify_integrity(const zkv_risc0* h, const uint8_t* seal, size_t seal_len, const uint8_t claim_digest[32], uint8_t* status_out) {
+    uint64_t off[2] = {0, seal_len}; uint8_t dummy = 0;
+    return risc0_batch(h, seal ? seal : &dummy, off, claim_digest, nullptr, 1, 1, status_out);
+}
+static uint32_t sel_le(const uint8_t s[4]) { return (uint32_t)s[0] | (uint32_t)s[1] << 8 | (uint32_t)s[2] << 16 | (uint32_t)s[3] << 24; }
+extern "C" int zkv_risc0_verify_batch_device(const zkv_risc0* h, int device, const void* d_seals260, const void* d_image_ids, const void* d_journal_digests, size_t n, void* d_status_out, void* stream) {
+    if (!h || !d_seals260 || !d_image_ids || !d_journal_digests || !d_status_out) return fail(ZKV_ERR_ARG, "zkv_risc0_verify_batch_device: null argument");
+    DevCtx* c = vk_ctx(h->vk, device);
+    if (!c) return fail(ZKV_ERR_ARG, "device not in the handle's device list");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(device));
+    if (!h->initialized) { CK(cudaMemsetAsync(d_status_out, ZKV_INVALID_INITIALIZATION, n, (cudaStream_t)stream)); return 0; }
+    if (n > MAX_CHUNK * 8) return fail(ZKV_ERR_ARG, "device batch too large");
+    Job j; memset(&j, 0, sizeof j);
+    j.vk = h->vk; j.n = n; j.recs = (const uint8_t*)d_seals260; j.stride = 260; j.off = 4; j.check_selector = 1; j.selector_le = sel_le(h->selector);
+    j.mode = SIG_RISC0_VERIFY; j.sig_a = (const uint8_t*)d_image_ids; j.sig_b = (const uint8_t*)d_journal_digests; j.hc = h->hc; j.base = h->base; j.all_fail = h->all_fail;
+    j.d_status = (uint8_t*)d_status_out;
+    cudaStream_t keep = c->stream; if (stream) c->stream = (cudaStream_t)stream;
+    int rc = run_verify(c, j);
+    c->stream = keep;
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------ SP1
+struct zkv_sp1 { const zkv_vk* vk = nullptr; zkv_vk* owned = nullptr; uint8_t verifier_hash[32]; };
+extern "C" int zkv_sp1_create(const zkv_vk* vk_or_null, const int* devices, int n_dev, zkv_sp1** out) {
+    if (!out) return fail(ZKV_ERR_ARG, "zkv_sp1_create: null out");
+    zkv_sp1* h = new zkv_sp1();
+    memcpy(h->verifier_hash, ZKV_SP1_VERIFIER_HASH, 32);
+    if (vk_or_null) { if (vk_or_null->n_ic != 3 || vk_or_null->vm != ZKV_VM_SP1) { delete h; return fail(ZKV_ERR_ARG, "zkv_sp1_create: need a ZKV_VM_SP1 key with 3 IC points"); } h->vk = vk_or_null; }
+    else { int rc = zkv_vk_load_sp1(devices, n_dev, &h->owned); if (rc) { delete h; return rc; } h->vk = h->owned; }
+    *out = h; return 0;
+}
+extern "C" void zkv_sp1_destroy(zkv_sp1* h) { if (!h) return; if (h->owned) zkv_vk_free(h->owned); delete h; }
+extern "C" int zkv_sp1_verifier_hash(const zkv_sp1* h, uint8_t out[32]) { if (!h || !out) return fail(ZKV_ERR_ARG, "null"); memcpy(out, h->verifier_hash, 32); return 0; }
+extern "C" const char* zkv_sp1_version(const zkv_sp1*) { return ZKV_SP1_VERSION; }
+
+extern "C" int zkv_sp1_verify_batch(const zkv_sp1* h, const uint8_t* vkeys, const uint8_t* public_values, const uint64_t* pv_off, const uint8_t* proofs, const uint64_t* proof_off, size_t n, uint8_t* status_out) {
+    if (!h || (n && (!vkeys || !public_values || !pv_off || !proofs || !proof_off || !status_out))) return fail(ZKV_ERR_ARG, "zkv_sp1_verify_batch: null argument");
+    if (n == 0) return 0;
+    if (n > 0xffffffffull) return fail(ZKV_ERR_ARG, "batch too large");
+    std::vector<uint32_t> cand; front_filter(proofs, proof_off, n, h->verifier_hash, status_out, cand);
+    const zkv_vk* vk = h->vk;
+    return for_each_device(vk, cand.size(), [&](DevCtx* c, size_t b, size_t e) -> int {
+        for (size_t s0 = b; s0 < e; s0 += MAX_CHUNK) {
+            size_t m = std::min(MAX_CHUNK, e - s0);
+            size_t pvb = 0; for (size_t t = 0; t < m; t++) { size_t i = cand[s0 + t]; pvb += pv_off[i + 1] - pv_off[i]; }
+            size_t rb = m * 256, kb = m * 32, ob = (m + 1) * 8, pv_at = rb + kb + ob;
+            int rc = ctx_stage(c, pv_at + pvb + 8, m); if (rc) return rc;
+            uint8_t* pr = c->h_pin; uint8_t* pk = pr + rb; uint64_t* po = (uint64_t*)(pk + kb); uint8_t* pp = c->h_pin + pv_at;
+            uint64_t acc = 0;
+            for (size_t t = 0; t < m; t++) {
+                size_t i = cand[s0 + t]; uint64_t len = pv_off[i + 1] - pv_off[i];
+                memcpy(pr + t * 256, proofs + proof_off[i] + 4, 256); memcpy(pk + t * 32, vkeys + i * 32, 32);
+                po[t] = acc; memcpy(pp + acc, public_values + pv_off[i], len); acc += len;
+            }
+            po[m] = acc;
+            CK(cudaMemcpyAsync(c->d_in, c->h_pin, pv_at + pvb, cudaMemcpyHostToDevice, c->stream));
+            Job j; memset(&j, 0, sizeof j);
+            j.vk = vk; j.n = m; j.recs = c->d_in; j.stride = 256; j.off = 0; j.mode = SIG_SP1; j.sig_a = c->d_in + rb; j.sig_b = c->d_in + pv_at;
+            j.pv_off = (const uint64_t*)(c->d_in + rb + kb); j.base = c->h_ic0; j.d_status = c->d_out;
+            rc = run_verify(c, j); if (rc) return rc;
+            CK(cudaMemcpyAsync(c->h_out, c->d_out, m, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            collect_stage_ms(c);
+            for (size_t t = 0; t < m; t++) status_out[cand[s0 + t]] = c->h_out[t];
+        }
+        return 0;
+    });
+}
+extern "C" int zkv_sp1_verify_proof(const zkv_sp1* h, const uint8_t vkey[32], const uint8_t* public_values, size_t pv_len, const uint8_t* proof, size_t proof_len, uint8_t* status_out) {
+    uint64_t po[2] = {0, proof_len}, vo[2] = {0, pv_len}; uint8_t dummy = 0;
+    return zkv_sp1_verify_batch(h, vkey, public_values ? public_values : &dummy, vo, proof ? proof : &dummy, po, 1, status_out);
+}
+extern "C" int zkv_sp1_verify_batch_device(const zkv_sp1* h, int device, const void* d_vkeys, const void* d_public_values, size_t pv_stride, const void* d_proofs260, size_t n, void* d_status_out, void* stream) {
+    if (!h || !d_vkeys || !d_public_values || !d_proofs260 || !d_status_out) return fail(ZKV_ERR_ARG, "zkv_sp1_verify_batch_device: null argument");
+    DevCtx* c = vk_ctx(h->vk, device);
+    if (!c) return fail(ZKV_ERR_ARG, "device not in the handle's device list");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(device));
+    if (n > MAX_CHUNK * 8) return fail(ZKV_ERR_ARG, "device batch too large");
+    Job j; memset(&j, 0, sizeof j);
+    j.vk = h->vk; j.n = n; j.recs = (const uint8_t*)d_proofs260; j.stride = 260; j.off = 4; j.check_selector = 1; j.selector_le = sel_le(h->verifier_hash);
+    j.mode = SIG_SP1; j.sig_a = (const uint8_t*)d_vkeys; j.sig_b = (const uint8_t*)d_public_values; j.pv_off = nullptr; j.pv_stride = pv_stride; j.base = c->h_ic0;
+    j.d_status = (uint8_t*)d_status_out;
+    cudaStream_t keep = c->stream; if (stream) c->stream = (cudaStream_t)stream;
+    int rc = run_verify(c, j);
+    c->stream = keep;
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------ pairing service (0x08 seam)
+static int run_pairing4(DevCtx* c, const zkv_vk* vk, size_t n_, const uint8_t* d_g1s, const uint8_t* d_g2s, uint8_t* d_ok, uint8_t* d_gt, uint8_t* d_miller) {
+    int n = (int)n_;
+    int rc = ctx_reserve(c, n_, 8); if (rc) return rc;
+    cudaStream_t s = c->stream;
+    CK(cudaEventRecord(c->ev[0], s));
+    k_g1_decode4<<<nblk(n), TPB, 0, s>>>(n, d_g1s, d_g2s, c->px[0], c->py[0], c->px[1], c->py[1], c->px[2], c->py[2], c->px[3], c->py[3], c->qx, c->qy, c->flags);
+    CK(cudaEventRecord(c->ev[1], s)); CK(cudaEventRecord(c->ev[2], s));
+    if (!vk->valid) {   // a fixed G2 point is invalid: every call reverts
+        CK(cudaMemsetAsync(d_ok, 2, n_, s)); if (d_gt) CK(cudaMemsetAsync(d_gt, 0, n_ * 384, s)); if (d_miller) CK(cudaMemsetAsync(d_miller, 0, n_ * 384, s));
+        for (int e = 3; e < 6; e++) CK(cudaEventRecord(c->ev[e], s));
+        return 0;
+    }
+    k_g2_check<<<nblk(n), TPB, 0, s>>>(n, c->qx, c->qy, c->flags);
+    CK(cudaEventRecord(c->ev[3], s));
+    MillerArgs a; memset(&a, 0, sizeof a);
+    for (int j = 0; j < 4; j++) { a.px[j] = c->px[j]; a.py[j] = c->py[j]; }
+    a.qx = c->qx; a.qy = c->qy;
+    for (int j = 0; j < 3; j++) a.tabs[j] = c->d_lines + (size_t)j * ZKV_LINES_PER_G2;
+    a.nfixed = 3; a.pre = nullptr;
+    a.skip_bit[0] = F_SKIP0; a.skip_bit[1] = 0x20; a.skip_bit[2] = 0x40; a.skip_bit[3] = 0x80;
+    a.vk_skip = (uint8_t)((c->h_vk.g2_inf[0] ? 2 : 0) | (c->h_vk.g2_inf[1] ? 4 : 0) | (c->h_vk.g2_inf[2] ? 8 : 0));
+    k_miller<<<nblk(n), TPB, 0, s>>>(n, a, c->flags, c->f);
+    CK(cudaEventRecord(c->ev[4], s));
+    if (d_miller) k_f12_to_bytes<<<nblk(n), TPB, 0, s>>>(n, c->f, d_miller);
+    k_final_exp<<<nblk(n), TPB, 0, s>>>(n, c->f, c->flags, d_ok, d_gt, 1);
+    CK(cudaEventRecord(c->ev[5], s));
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int zkv_pairing4_batch(const zkv_vk* vk, const uint8_t* g1s, const uint8_t* g2s, size_t n, uint8_t* ok_out, uint8_t* gt_out, uint8_t* miller_out) {
+    if (!vk || (n && (!g1s || !g2s || !ok_out))) return fail(ZKV_ERR_ARG, "zkv_pairing4_batch: null argument");
+    if (n == 0) return 0;
+    const size_t CH = (size_t)1 << 18;
+    return for_each_device(vk, n, [&](DevCtx* c, size_t b, size_t e) -> int {
+        for (size_t s0 = b; s0 < e; s0 += CH) {
+            size_t m = std::min(CH, e - s0);
+            size_t ob = m + (gt_out ? m * 384 : 0) + (miller_out ? m * 384 : 0);
+            int rc = ctx_stage(c, m * 384, ob); if (rc) return rc;
+            memcpy(c->h_pin, g1s + s0 * 256, m * 256); memcpy(c->h_pin + m * 256, g2s + s0 * 128, m * 128);
+            CK(cudaMemcpyAsync(c->d_in, c->h_pin, m * 384, cudaMemcpyHostToDevice, c->stream));
+            uint8_t* d_gt = gt_out ? c->d_out + m : nullptr; uint8_t* d_ml = miller_out ? c->d_out + m + (gt_out ? m * 384 : 0) : nullptr;
+            rc = run_pairing4(c, vk, m, c->d_in, c->d_in + m * 256, c->d_out, d_gt, d_ml); if (rc) return rc;
+            CK(cudaMemcpyAsync(c->h_out, c->d_out, ob, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            collect_stage_ms(c);
+            memcpy(ok_out + s0, c->h_out, m);
+            if (gt_out) memcpy(gt_out + s0 * 384, c->h_out + m, m * 384);
+            if (miller_out) memcpy(miller_out + s0 * 384, c->h_out + m + (gt_out ? m * 384 : 0), m * 384);
+        }
+        return 0;
+    });
+}
+extern "C" int zkv_pairing4_batch_device(const zkv_vk* vk, int device, const void* d_g1s, const void* d_g2s, size_t n, void* d_ok_out, void* d_gt_out, void* stream) {
+    if (!vk || !d_g1s || !d_g2s || !d_ok_out) return fail(ZKV_ERR_ARG, "zkv_pairing4_batch_device: null argument");
+    DevCtx* c = vk_ctx(vk, device);
+    if (!c) return fail(ZKV_ERR_ARG, "device not in the key's device list");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(device));
+    cudaStream_t keep = c->stream; if (stream) c->stream = (cudaStream_t)stream;
+    int rc = run_pairing4(c, vk, n, (const uint8_t*)d_g1s, (const uint8_t*)d_g2s, (uint8_t*)d_ok_out, (uint8_t*)d_gt_out, nullptr);
+    c->stream = keep;
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------ hooks and small services
+extern "C" int zkv_vk_x_batch(const zkv_vk* vk, const uint8_t* signals, int k, size_t n, uint8_t* out_points) {
+    if (!vk || !signals || !out_points || k + 1 != vk->n_ic) return fail(ZKV_ERR_ARG, "zkv_vk_x_batch: bad argument");
+    if (n == 0) return 0;
+    DevCtx* c = vk->devs[0];
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    int rc = ctx_reserve(c, n, (size_t)k * 8); if (rc) return rc;
+    rc = ctx_stage(c, n * (size_t)k * 32, n * 64); if (rc) return rc;
+    CK(cudaMemcpyAsync(c->d_in, signals, n * (size_t)k * 32, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->flags, 0, n, c->stream));
+    k_generic_signals<<<nblk(n), TPB, 0, c->stream>>>((int)n, k, c->d_in, c->scal, c->flags);
+    k_vkx<<<nblk(n), TPB, 0, c->stream>>>((int)n, c->scal, k, ZKV_WIN_PER_SCALAR, c->d_tab, c->h_ic0, c->px[2], c->py[2], c->flags);
+    k_points_to_bytes<<<nblk(n), TPB, 0, c->stream>>>((int)n, c->px[2], c->py[2], c->d_out);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_points, c->d_out, n * 64, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// stand-alone scratch launcher for the stateless services below
+template <class L>
+static int with_scratch(int device, const void* in0, size_t b0, const void* in1, size_t b1, void* out0, size_t ob0, void* out1, size_t ob1, L launch) {
+    if (zkv_device_count() <= device || device < 0) return fail(ZKV_ERR_CUDA, "no such CUDA device (this library has no CPU path)");
+    CK(cudaSetDevice(device));
+    uint8_t *d0 = nullptr, *d1 = nullptr, *o0 = nullptr, *o1 = nullptr;
+    CK(cudaMalloc(&d0, b0 + 16)); CK(cudaMalloc(&d1, b1 + 16)); CK(cudaMalloc(&o0, ob0 + 16)); CK(cudaMalloc(&o1, ob1 + 16));
+    CK(cudaMemcpy(d0, in0, b0, cudaMemcpyHostToDevice)); if (b1) CK(cudaMemcpy(d1, in1, b1, cudaMemcpyHostToDevice));
+    launch(d0, d1, o0, o1);
+    cudaError_t e = cudaGetLastError(); if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) { e = cudaMemcpy(out0, o0, ob0, cudaMemcpyDeviceToHost); if (e == cudaSuccess && ob1) e = cudaMemcpy(out1, o1, ob1, cudaMemcpyDeviceToHost); }
+    cudaFree(d0); cudaFree(d1); cudaFree(o0); cudaFree(o1);
+    if (e != cudaSuccess) return fail(ZKV_ERR_CUDA, cudaGetErrorString(e));
+    return 0;
+}
+extern "C" int zkv_fp_mul_batch(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out, int device) {
+    if (!a || !b || !out) return fail(ZKV_ERR_ARG, "null");
+    if (n == 0) return 0;
+    uint8_t dummy;
+    return with_scratch(device, a, n * 32, b, n * 32, out, n * 32, &dummy, 0, [&](uint8_t* d0, uint8_t* d1, uint8_t* o0, uint8_t*) { k_fp_mul_bytes<<<nblk(n), TPB>>>((int)n, d0, d1, o0); });
+}
+extern "C" int zkv_g2_check_batch(const uint8_t* g2s, size_t n, uint8_t* out, int device) {
+    if (!g2s || !out) return fail(ZKV_ERR_ARG, "null");
+    if (n == 0) return 0;
+    uint8_t dummy;
+    return with_scratch(device, g2s, n * 128, &dummy, 0, out, n, &dummy, 0, [&](uint8_t* d0, uint8_t*, uint8_t* o0, uint8_t*) { k_g2_check_bytes<<<nblk(n), TPB>>>((int)n, d0, o0); });
+}
+extern "C" int zkv_ec_add_batch(const uint8_t* in, size_t n, uint8_t* out, uint8_t* reverted, int device) {
+    if (!in || !out || !reverted) return fail(ZKV_ERR_ARG, "null");
+    if (n == 0) return 0;
+    uint8_t dummy;
+    return with_scratch(device, in, n * 128, &dummy, 0, out, n * 64, reverted, n, [&](uint8_t* d0, uint8_t*, uint8_t* o0, uint8_t* o1) { k_ec_add<<<nblk(n), TPB>>>((int)n, d0, o0, o1); });
+}
+extern "C" int zkv_ec_mul_batch(const uint8_t* in, size_t n, uint8_t* out, uint8_t* reverted, int device) {
+    if (!in || !out || !reverted) return fail(ZKV_ERR_ARG, "null");
+    if (n == 0) return 0;
+    uint8_t dummy;
+    return with_scratch(device, in, n * 96, &dummy, 0, out, n * 64, reverted, n, [&](uint8_t* d0, uint8_t*, uint8_t* o0, uint8_t* o1) { k_ec_mul<<<nblk(n), TPB>>>((int)n, d0, o0, o1); });
+}
+extern "C" int zkv_g2_mul_batch(const uint8_t* points, int broadcast_point, const uint8_t* scalars, size_t n, uint8_t* out, uint8_t* reverted, int device) {
+    if (!points || !scalars || !out || !reverted) return fail(ZKV_ERR_ARG, "null");
+    if (n == 0) return 0;
+    return with_scratch(device, points, broadcast_point ? 128 : n * 128, scalars, n * 32, out, n * 128, reverted, n,
+                        [&](uint8_t* d0, uint8_t* d1, uint8_t* o0, uint8_t* o1) { k_g2_mul<<<nblk(n), TPB>>>((int)n, d0, broadcast_point, d1, o0, o1); });
+}
+extern "C" int zkv_last_stage_ms(const void* handle_vk, int device, float* out, int cap) {
+    const zkv_vk* vk = (const zkv_vk*)handle_vk;
+    if (!vk || !out) return fail(ZKV_ERR_ARG, "null");
+    DevCtx* c = vk_ctx(vk, device);
+    if (!c) return fail(ZKV_ERR_ARG, "device not in the key's device list");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (cudaSetDevice(device) == cudaSuccess) { cudaEventSynchronize(c->ev[5]); collect_stage_ms(c); }
+    int m = std::min(cap, 5);
+    for (int i = 0; i < m; i++) out[i] = c->stage_ms[i];
+    return m;
+}
+extern "C" const void* zkv_risc0_vk(const zkv_risc0* h) { return h ? h->vk : nullptr; }
+extern "C" const void* zkv_sp1_vk(const zkv_sp1* h) { return h ? h->vk : nullptr; }
+
+extern "C" int zkv_imad_peak(int device, double* wide_per_s, double* fpmul_per_s) {
+    if (zkv_device_count() <= device || device < 0) return fail(ZKV_ERR_CUDA, "no such CUDA device");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+    int blocks = prop.multiProcessorCount * 8, threads = 256;
+    uint64_t* d_out; fp* d_fp;
+    CK(cudaMalloc(&d_out, (size_t)blocks * threads * 8)); CK(cudaMalloc(&d_fp, (size_t)blocks * threads * sizeof(fp)));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best_w = 1e30f, best_f = 1e30f;
+    const int it_w = 4096, it_f = 2048;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(e0)); k_imad_wide<<<blocks, threads>>>(d_out, 0x9e3779b9u, 0x7f4a7c15u, it_w); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep) best_w = std::min(best_w, ms);
+        CK(cudaEventRecord(e0)); k_fpmul_chain<<<blocks, threads>>>(d_fp, it_f); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep) best_f = std::min(best_f, ms);
+    }
+    CK(cudaGetLastError());
+    if (wide_per_s) *wide_per_s = (double)blocks * threads * it_w * 64.0 / (best_w * 1e-3);
+    if (fpmul_per_s) *fpmul_per_s = (double)blocks * threads * it_f * 2.0 / (best_f * 1e-3);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out); cudaFree(d_fp);
+    return 0;
+}

@@ -1,0 +1,59 @@
+// TEST INFRASTRUCTURE: compiles csrc/bn254.cuh as plain C++ (portable Fp backend) so the tower / curve /
+// pairing logic the kernels use can be compared with the oracle on a CPU-only box.  Never shipped.
+#include <cstring>
+#include "../../stylus_zkvm_verifiers_b200/csrc/bn254.cuh"
+using namespace zkv;
+
+static bool dec_fp(fp& r, const uint8_t* b) { fp t; be32_to_raw(t.v, b); if (u256_geq(t.v, C_P)) return false; fp_to_mont(r, t); return true; }
+static bool dec_g2(fp2& x, fp2& y, const uint8_t* b) { return dec_fp(x.c1, b) && dec_fp(x.c0, b + 32) && dec_fp(y.c1, b + 64) && dec_fp(y.c0, b + 96); }
+static void dec_f12(fp12& a, const uint8_t* in) { fp* w = &a.c0.c0.c0; for (int i = 0; i < 12; i++) dec_fp(w[i], in + 32 * i); }
+
+extern "C" {
+int emu_fp_mul(const uint8_t* a, const uint8_t* b, uint8_t* out) { fp x, y, z; dec_fp(x, a); dec_fp(y, b); fp_mul(z, x, y); fp_to_be32(out, z); return 0; }
+int emu_fp_inv(const uint8_t* a, uint8_t* out) { fp x, z; dec_fp(x, a); fp_inv(z, x); fp_to_be32(out, z); return 0; }
+int emu_f12_mul(const uint8_t* a, const uint8_t* b, uint8_t* out) { fp12 x, y, z; dec_f12(x, a); dec_f12(y, b); f12_mul(z, x, y); f12_to_bytes(out, z); return 0; }
+int emu_f12_sqr(const uint8_t* a, uint8_t* out) { fp12 x, z; dec_f12(x, a); f12_sqr(z, x); f12_to_bytes(out, z); return 0; }
+int emu_f12_cyc_sqr(const uint8_t* a, uint8_t* out) { fp12 x, z; dec_f12(x, a); f12_cyc_sqr(z, x); f12_to_bytes(out, z); return 0; }
+int emu_f12_inv(const uint8_t* a, uint8_t* out) { fp12 x, z; dec_f12(x, a); f12_inv(z, x); f12_to_bytes(out, z); return 0; }
+int emu_final_exp(const uint8_t* a, uint8_t* out) { fp12 x, z; dec_f12(x, a); final_exp(z, x); f12_to_bytes(out, z); return 0; }
+// 1 = in G2, 0 = on twist but not in G2, 2 = not on twist / bad encoding
+int emu_g2_check(const uint8_t* q) { fp2 x, y; if (!dec_g2(x, y, q)) return 2; if (!g2_on_curve(x, y)) return 2; return g2_in_subgroup(x, y) ? 1 : 0; }
+// 4-pair Miller loop + final exp the way k_miller does it: pair 0 variable G2, pairs 1..3 from line tables of the three fixed points
+int emu_pairing4(const uint8_t* g1s /*4x64*/, const uint8_t* g2 /*128*/, const uint8_t* fixed /*3x128*/, uint8_t* miller_out, uint8_t* gt_out) {
+    static line_t tabs_store[3][ZKV_LINES_PER_G2];
+    fp px[4], py[4];
+    for (int j = 0; j < 4; j++) { dec_fp(px[j], g1s + 64 * j); dec_fp(py[j], g1s + 64 * j + 32); }
+    fp2 qx, qy; dec_g2(qx, qy, g2);
+    const line_t* tabs[3];
+    for (int j = 0; j < 3; j++) { fp2 x, y; dec_g2(x, y, fixed + 128 * j); g2_precompute_lines(tabs_store[j], x, y); tabs[j] = tabs_store[j]; }
+    fp12 f, gt;
+    miller_loop(f, px, py, qx, qy, tabs, 3, 0);
+    final_exp(gt, f);
+    f12_to_bytes(miller_out, f); f12_to_bytes(gt_out, gt);
+    return f12_is_one(gt) ? 1 : 0;
+}
+// 3-pair loop times a precomputed Miller(alpha, beta), as run_verify does
+int emu_pairing3_pre(const uint8_t* g1s /*4x64: A, alpha, vkx, C*/, const uint8_t* g2, const uint8_t* fixed, uint8_t* miller_out) {
+    static line_t tabs_store[3][ZKV_LINES_PER_G2];
+    fp px[4], py[4];
+    for (int j = 0; j < 4; j++) { dec_fp(px[j], g1s + 64 * j); dec_fp(py[j], g1s + 64 * j + 32); }
+    fp2 qx, qy; dec_g2(qx, qy, g2);
+    for (int j = 0; j < 3; j++) { fp2 x, y; dec_g2(x, y, fixed + 128 * j); g2_precompute_lines(tabs_store[j], x, y); }
+    fp12 pre, f;
+    { fp ax[2] = {fp_zero(), px[1]}, ay[2] = {fp_zero(), py[1]}; const line_t* t1[1] = {tabs_store[0]}; fp2 z = f2_zero(); miller_loop(pre, ax, ay, z, z, t1, 1, 1u); }
+    fp bx[3] = {px[0], px[2], px[3]}, by[3] = {py[0], py[2], py[3]};
+    const line_t* t2[2] = {tabs_store[1], tabs_store[2]};
+    miller_loop(f, bx, by, qx, qy, t2, 2, 0);
+    f12_mul(f, f, pre);
+    f12_to_bytes(miller_out, f);
+    return 0;
+}
+// scalar multiple by double-and-add with the complete mixed addition used by k_vkx / k_ec_mul
+int emu_g1_mul(const uint8_t* pt, const uint8_t* k, uint8_t* out) {
+    fp x, y; dec_fp(x, pt); dec_fp(y, pt + 32);
+    uint32_t s[8]; be32_to_raw(s, k);
+    g1j acc; acc.x = fp_one(); acc.y = fp_one(); acc.z = fp_zero();
+    for (int b = 255; b >= 0; b--) { g1j d; g1_dbl(d, acc); acc = d; if ((s[b >> 5] >> (b & 31)) & 1u) g1_add_affine(acc, x, y); }
+    fp ox, oy; g1_to_affine(ox, oy, acc); fp_to_be32(out, ox); fp_to_be32(out + 32, oy); return 0;
+}
+}

@@ -1,0 +1,110 @@
+"""CPU-side check of the arithmetic the kernels are built from: csrc/bn254.cuh compiled as plain C++
+(tests/host_emu/emu.cpp) against the oracle, and the PTX instruction lists of csrc/fp_ptx.cuh simulated
+against Python integers (tools/gen_fp_ptx.py --check)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import pytest
+
+import oracle_lib as O
+from stylus_zkvm_verifiers_b200.synth import G2_GEN, SplitMix64, random_twist_point
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+w32 = O.w32
+G1 = w32(1) + w32(2)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    d = os.path.join(ROOT, "tests", "host_emu")
+    so = os.path.join(d, "libzkv_emu.so")
+    srcs = [os.path.join(d, "emu.cpp")] + [os.path.join(ROOT, "stylus_zkvm_verifiers_b200", "csrc", f) for f in ("bn254.cuh", "bn254_consts.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, srcs[0]])
+    return C.CDLL(so)
+
+
+def rand_f12(rng):
+    return b"".join(w32(rng.u256() % P) for _ in range(12))
+
+
+def test_ptx_instruction_lists_simulate_correctly():
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_fp_ptx.py"), "--check"])
+
+
+def test_generated_header_is_current():
+    """csrc/fp_ptx.cuh must be exactly what the (verified) generator emits."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_fp_ptx", os.path.join(ROOT, "tools", "gen_fp_ptx.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    assert open(os.path.join(ROOT, "stylus_zkvm_verifiers_b200", "csrc", "fp_ptx.cuh")).read() == g.render()
+
+
+def test_fp_and_fp12_ops(emu):
+    rng = SplitMix64(11)
+    out = C.create_string_buffer(384)
+    for _ in range(50):
+        a, b = rng.u256() % P, rng.u256() % P
+        emu.emu_fp_mul(w32(a), w32(b), out); assert out.raw[:32] == w32(a * b % P)
+        emu.emu_fp_inv(w32(a), out); assert out.raw[:32] == w32(pow(a, -1, P))
+    for _ in range(10):
+        x, y = rand_f12(rng), rand_f12(rng)
+        emu.emu_f12_mul(x, y, out); assert out.raw == O.fp12_mul(x, y)
+        emu.emu_f12_sqr(x, out); assert out.raw == O.fp12_mul(x, x)
+        emu.emu_f12_inv(x, out); inv = out.raw
+        one = w32(1) + bytes(352)
+        assert O.fp12_mul(x, inv) == one
+
+
+def test_final_exp_and_cyclotomic(emu):
+    rng = SplitMix64(12)
+    out = C.create_string_buffer(384)
+    for _ in range(3):
+        m = rand_f12(rng)
+        emu.emu_final_exp(m, out); gt = out.raw
+        assert gt == O.final_exp(m)
+        emu.emu_f12_cyc_sqr(gt, out)                                  # GT is in the cyclotomic subgroup
+        assert out.raw == O.fp12_mul(gt, gt) == O.fp12_cyc_sqr(gt)
+
+
+def test_g2_subgroup_test_matches_oracle(emu):
+    rng = SplitMix64(13)
+    for k in (1, 2, 3, R - 1, rng.fr(), rng.fr()):
+        assert emu.emu_g2_check(O.g2_mul(G2_GEN, k)) == 1
+    for _ in range(6):
+        q = random_twist_point(rng)
+        assert O.ec_pairing(G1 + q) is None                           # oracle: [r]Q != inf -> revert
+        assert emu.emu_g2_check(q) == 0
+        # small-order component: add a subgroup point; still outside G2
+        assert emu.emu_g2_check(O.g2_add(q, O.g2_mul(G2_GEN, rng.fr()))) == 0
+    bad = bytearray(G2_GEN); bad[100] ^= 4
+    assert emu.emu_g2_check(bytes(bad)) == 2
+
+
+def test_pairing_values_bit_exact(emu, consts):
+    rng = SplitMix64(14)
+    h = bytes.fromhex
+    vkj = consts["risc0_vk"]
+    fixed = b"".join(h(vkj[n][i][j]) for n in ("beta", "gamma", "delta") for i in range(2) for j in range(2))
+    mo, go, m3 = C.create_string_buffer(384), C.create_string_buffer(384), C.create_string_buffer(384)
+    for _ in range(3):
+        g1s = b"".join(O.g1_mul(G1, rng.fr()) for _ in range(4))
+        q = O.g2_mul(G2_GEN, rng.fr())
+        data = g1s[0:64] + q + g1s[64:128] + fixed[0:128] + g1s[128:192] + fixed[128:256] + g1s[192:256] + fixed[256:384]
+        ret, m, gt = O.ec_pairing(data, debug=True)
+        ok = emu.emu_pairing4(g1s, q, fixed, mo, go)
+        assert mo.raw == m and go.raw == gt and ok == ret[31]
+        emu.emu_pairing3_pre(g1s, q, fixed, m3)                        # 3-pair loop x precomputed Miller(alpha, beta): same field element
+        assert m3.raw == m
+
+
+def test_g1_scalar_mul(emu):
+    rng = SplitMix64(15)
+    out = C.create_string_buffer(64)
+    for k in (0, 1, 2, R - 1, R, R + 5, (1 << 256) - 1, rng.u256(), rng.u256()):
+        emu.emu_g1_mul(G1, w32(k), out)
+        assert out.raw == O.ec_mul(G1 + w32(k))
