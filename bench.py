@@ -199,8 +199,10 @@ def main():
         W_M = W_SP1_M
     d_st = torch.full((n,), 255, dtype=torch.uint8, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()                 # a real (non-null) stream: the library enqueues its kernels on the stream it is given
+    torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
+    assert sp != 0
 
     def barrier():
         torch.cuda.synchronize()

@@ -185,7 +185,10 @@ struct MillerArgs {
     uint8_t skip_bit[4];      // which flag bit disables pair j (0 = never)
     uint8_t vk_skip;          // pairs disabled for the whole batch (a vk G2 point at infinity)
 };
-__global__ void __launch_bounds__(128) k_miller(int n, MillerArgs a, const uint8_t* flags, fp12* out) {
+#ifndef ZKV_MINBLOCKS
+#define ZKV_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(128, ZKV_MINBLOCKS) k_miller(int n, MillerArgs a, const uint8_t* flags, fp12* out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint8_t fl = flags[i];
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(128) k_miller(int n, MillerArgs a, const uint8
 }
 
 // K7 + K8: final exponentiation, is-one test and status byte
-__global__ void __launch_bounds__(128) k_final_exp(int n, const fp12* in, const uint8_t* flags, uint8_t* status, uint8_t* gt_out, int pairing_mode) {
+__global__ void __launch_bounds__(128, ZKV_MINBLOCKS) k_final_exp(int n, const fp12* in, const uint8_t* flags, uint8_t* status, uint8_t* gt_out, int pairing_mode) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint8_t fl = flags[i];
