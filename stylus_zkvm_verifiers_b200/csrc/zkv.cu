@@ -129,7 +129,7 @@ static int vk_build_on(zkv_vk* vk, DevCtx* c) {
     VkDev init; memset(&init, 0, sizeof init); init.valid = 1;
     CK(cudaMemcpyAsync(c->d_vk, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemsetAsync(c->d_lines, 0, sizeof(line_t) * 3 * ZKV_LINES_PER_G2, c->stream));
-    k_vk_setup<<<1, 4, 0, c->stream>>>(d_bytes, d_bytes + 64, c->d_vk, c->d_lines);
+    k_vk_setup<<<4, 1, 0, c->stream>>>(d_bytes, d_bytes + 64, c->d_vk, c->d_lines);
     k_ic_tables<<<nt, ZKV_WIN_PER_SCALAR, 0, c->stream>>>(d_bytes + 448, c->d_tab, c->d_ic0, c->d_vk);
     k_vk_miller_ab<<<1, 1, 0, c->stream>>>(c->d_vk, c->d_lines, c->d_pre);
     CK(cudaGetLastError());
@@ -228,9 +228,9 @@ static int run_verify(DevCtx* c, const Job& j) {
     a.nfixed = 2; a.pre = c->d_pre;
     a.skip_bit[0] = F_SKIP0; a.skip_bit[1] = F_SKIPX; a.skip_bit[2] = F_SKIPC;
     a.vk_skip = (uint8_t)((c->h_vk.g2_inf[1] ? 2 : 0) | (c->h_vk.g2_inf[2] ? 4 : 0));
-    k_miller<<<nblk(n), TPB, 0, s>>>(n, a, c->flags, c->f);
+    k_miller<<<nblk(n, ZKV_HTPB), ZKV_HTPB, 0, s>>>(n, a, c->flags, c->f);
     CK(cudaEventRecord(c->ev[4], s));
-    k_final_exp<<<nblk(n), TPB, 0, s>>>(n, c->f, c->flags, j.d_status, nullptr, 0);
+    k_final_exp<<<nblk(n, ZKV_HTPB), ZKV_HTPB, 0, s>>>(n, c->f, c->flags, j.d_status, nullptr, 0);
     CK(cudaEventRecord(c->ev[5], s));
     CK(cudaGetLastError());
     return 0;
@@ -542,10 +542,10 @@ static int run_pairing4(DevCtx* c, const zkv_vk* vk, size_t n_, const uint8_t* d
     a.nfixed = 3; a.pre = nullptr;
     a.skip_bit[0] = F_SKIP0; a.skip_bit[1] = 0x20; a.skip_bit[2] = 0x40; a.skip_bit[3] = 0x80;
     a.vk_skip = (uint8_t)((c->h_vk.g2_inf[0] ? 2 : 0) | (c->h_vk.g2_inf[1] ? 4 : 0) | (c->h_vk.g2_inf[2] ? 8 : 0));
-    k_miller<<<nblk(n), TPB, 0, s>>>(n, a, c->flags, c->f);
+    k_miller<<<nblk(n, ZKV_HTPB), ZKV_HTPB, 0, s>>>(n, a, c->flags, c->f);
     CK(cudaEventRecord(c->ev[4], s));
     if (d_miller) k_f12_to_bytes<<<nblk(n), TPB, 0, s>>>(n, c->f, d_miller);
-    k_final_exp<<<nblk(n), TPB, 0, s>>>(n, c->f, c->flags, d_ok, d_gt, 1);
+    k_final_exp<<<nblk(n, ZKV_HTPB), ZKV_HTPB, 0, s>>>(n, c->f, c->flags, d_ok, d_gt, 1);
     CK(cudaEventRecord(c->ev[5], s));
     CK(cudaGetLastError());
     return 0;

@@ -1,10 +1,11 @@
 // TEST INFRASTRUCTURE: compiles csrc/bn254.cuh as plain C++ (portable Fp backend) so the tower / curve /
 // pairing logic the kernels use can be compared with the oracle on a CPU-only box.  Never shipped.
 #include <cstring>
+#include <cstdio>
 #include "../../stylus_zkvm_verifiers_b200/csrc/bn254.cuh"
 using namespace zkv;
 
-static bool dec_fp(fp& r, const uint8_t* b) { fp t; be32_to_raw(t.v, b); if (u256_geq(t.v, C_P)) return false; fp_to_mont(r, t); return true; }
+static bool dec_fp(fp& r, const uint8_t* b) { uint32_t w[8]; be32_to_raw(w, b); if (u256_geq(w, C_PW)) return false; fp_from_raw_mont(r, w); return true; }
 static bool dec_g2(fp2& x, fp2& y, const uint8_t* b) { return dec_fp(x.c1, b) && dec_fp(x.c0, b + 32) && dec_fp(y.c1, b + 64) && dec_fp(y.c0, b + 96); }
 static void dec_f12(fp12& a, const uint8_t* in) { fp* w = &a.c0.c0.c0; for (int i = 0; i < 12; i++) dec_fp(w[i], in + 32 * i); }
 
@@ -40,7 +41,7 @@ int emu_pairing3_pre(const uint8_t* g1s /*4x64: A, alpha, vkx, C*/, const uint8_
     fp2 qx, qy; dec_g2(qx, qy, g2);
     for (int j = 0; j < 3; j++) { fp2 x, y; dec_g2(x, y, fixed + 128 * j); g2_precompute_lines(tabs_store[j], x, y); }
     fp12 pre, f;
-    { fp ax[2] = {fp_zero(), px[1]}, ay[2] = {fp_zero(), py[1]}; const line_t* t1[1] = {tabs_store[0]}; fp2 z = f2_zero(); miller_loop(pre, ax, ay, z, z, t1, 1, 1u); }
+    { fp ax[2] = {fp_zero(), px[1]}, ay[2] = {fp_zero(), py[1]}; const line_t* t1[1] = {tabs_store[0]}; fp2 z = f2_zero(); miller_loop(pre, ax, ay, z, z, t1, 1, 1u);   /* pair 0 switched off: only the tabled (alpha, beta) pair contributes */ }
     fp bx[3] = {px[0], px[2], px[3]}, by[3] = {py[0], py[2], py[3]};
     const line_t* t2[2] = {tabs_store[1], tabs_store[2]};
     miller_loop(f, bx, by, qx, qy, t2, 2, 0);

@@ -103,6 +103,329 @@ __global__ void k_wide_alu(uint64_t* out, uint32_t a0, uint32_t b0, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ s0 ^ s1 ^ s2 ^ s3;
 }
 
+// signed mad.wide.s32, 9 independent columns x 9 rows with all-distinct multiplicands (the operand pattern of the 29-bit-limb multiplier)
+__global__ void k_swide_9x9(int64_t* out, int32_t a0, int32_t b0, int iters) {
+    int32_t a[9], b[9];
+    for (int i = 0; i < 9; i++) { a[i] = a0 * (i + 1) + threadIdx.x; b[i] = b0 * (i + 3) - blockIdx.x; }
+    int64_t t[17];
+    for (int i = 0; i < 17; i++) t[i] = i;
+    for (int k = 0; k < iters; k++) {
+#pragma unroll
+        for (int i = 0; i < 9; i++)
+#pragma unroll
+            for (int j = 0; j < 9; j++) t[i + j] += (int64_t)a[i] * b[j];
+        a[0] ^= (int32_t)t[8];      // keep the loop from being hoisted
+    }
+    int64_t x = 0;
+    for (int i = 0; i < 17; i++) x ^= t[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+// same, unsigned
+__global__ void k_uwide_9x9(uint64_t* out, uint32_t a0, uint32_t b0, int iters) {
+    uint32_t a[9], b[9];
+    for (int i = 0; i < 9; i++) { a[i] = a0 * (i + 1) + threadIdx.x; b[i] = b0 * (i + 3) - blockIdx.x; }
+    uint64_t t[17];
+    for (int i = 0; i < 17; i++) t[i] = i;
+    for (int k = 0; k < iters; k++) {
+#pragma unroll
+        for (int i = 0; i < 9; i++)
+#pragma unroll
+            for (int j = 0; j < 9; j++) t[i + j] += (uint64_t)a[i] * b[j];
+        a[0] ^= (uint32_t)t[8];
+    }
+    uint64_t x = 0;
+    for (int i = 0; i < 17; i++) x ^= t[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+// unsigned products by the limbs of p as IMMEDIATES (how the reduction rows compile when p is a literal): 8 independent columns
+__global__ void k_uwide_imm(uint64_t* out, uint32_t a0, int iters) {
+    uint32_t m[8];
+    for (int r = 0; r < 8; r++) m[r] = (uint32_t)out[r + (threadIdx.x & 1)] | 0x1000000u;
+    uint64_t t[8];
+    for (int i = 0; i < 8; i++) t[i] = i;
+    for (int k = 0; k < iters; k++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            t[0] += (uint64_t)m[r] * 0x187cfd47u; t[1] += (uint64_t)m[r] * 0x010460b6u; t[2] += (uint64_t)m[r] * 0x1c72a34fu; t[3] += (uint64_t)m[r] * 0x02d522d0u;
+            t[4] += (uint64_t)m[r] * 0x1585d978u; t[5] += (uint64_t)m[r] * 0x02db40c0u; t[6] += (uint64_t)m[r] * 0x00a6e141u; t[7] += (uint64_t)m[r] * 0x0e5c2634u;
+        }
+    }
+    uint64_t x = 0;
+    for (int i = 0; i < 8; i++) x ^= t[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+__constant__ uint32_t CP[9] = {0x187cfd47u, 0x010460b6u, 0x1c72a34fu, 0x02d522d0u, 0x1585d978u, 0x02db40c0u, 0x00a6e141u, 0x0e5c2634u, 0x0030644eu};
+// same with p's limbs read from the constant bank (compiles to uniform-register operands)
+__global__ void k_uwide_cbank(uint64_t* out, uint32_t a0, int iters) {
+    uint32_t m[8];
+    for (int r = 0; r < 8; r++) m[r] = (uint32_t)out[r + (threadIdx.x & 1)] | 0x1000000u;
+    uint64_t t[8];
+    for (int i = 0; i < 8; i++) t[i] = i;
+    for (int k = 0; k < iters; k++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) t[j] += (uint64_t)m[r] * CP[j];
+    }
+    uint64_t x = 0;
+    for (int i = 0; i < 8; i++) x ^= t[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+// same with p's limbs in per-thread vector registers
+__global__ void k_uwide_regs(uint64_t* out, uint32_t a0, int iters) {
+    uint32_t m[8], p[8];
+    for (int r = 0; r < 8; r++) { m[r] = (uint32_t)out[r + (threadIdx.x & 1)] | 0x1000000u; p[r] = (uint32_t)out[r + 9 + (threadIdx.x & 1)] | 0x10000000u; }
+    uint64_t t[8];
+    for (int i = 0; i < 8; i++) t[i] = i;
+    for (int k = 0; k < iters; k++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) t[j] += (uint64_t)m[r] * p[j];
+    }
+    uint64_t x = 0;
+    for (int i = 0; i < 8; i++) x ^= t[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
+
+// every multiply takes the low word of its own accumulator as multiplicand, so nothing is loop invariant (reg)
+__global__ void k_asm_u32_rr(uint64_t* out, uint32_t a0, uint32_t b0, int iters) {
+    uint32_t b[8]; uint64_t c[16];
+    for (int i = 0; i < 8; i++) b[i] = (b0 * (i + 3) ^ blockIdx.x) | 1u;
+    for (int i = 0; i < 16; i++) c[i] = a0 * (i + 1) + threadIdx.x;
+    for (int k = 0; k < iters; k++) {
+        asm volatile("{\n\t.reg .b32 tl<16>, th<16>;\n\t"
+            "mov.b64 {tl0, th0}, %0;\n\t"
+            "mad.wide.u32 %0, tl0, %16, %0;\n\t"
+            "mov.b64 {tl1, th1}, %1;\n\t"
+            "mad.wide.u32 %1, tl1, %21, %1;\n\t"
+            "mov.b64 {tl2, th2}, %2;\n\t"
+            "mad.wide.u32 %2, tl2, %18, %2;\n\t"
+            "mov.b64 {tl3, th3}, %3;\n\t"
+            "mad.wide.u32 %3, tl3, %23, %3;\n\t"
+            "mov.b64 {tl4, th4}, %4;\n\t"
+            "mad.wide.u32 %4, tl4, %20, %4;\n\t"
+            "mov.b64 {tl5, th5}, %5;\n\t"
+            "mad.wide.u32 %5, tl5, %17, %5;\n\t"
+            "mov.b64 {tl6, th6}, %6;\n\t"
+            "mad.wide.u32 %6, tl6, %22, %6;\n\t"
+            "mov.b64 {tl7, th7}, %7;\n\t"
+            "mad.wide.u32 %7, tl7, %19, %7;\n\t"
+            "mov.b64 {tl8, th8}, %8;\n\t"
+            "mad.wide.u32 %8, tl8, %16, %8;\n\t"
+            "mov.b64 {tl9, th9}, %9;\n\t"
+            "mad.wide.u32 %9, tl9, %21, %9;\n\t"
+            "mov.b64 {tl10, th10}, %10;\n\t"
+            "mad.wide.u32 %10, tl10, %18, %10;\n\t"
+            "mov.b64 {tl11, th11}, %11;\n\t"
+            "mad.wide.u32 %11, tl11, %23, %11;\n\t"
+            "mov.b64 {tl12, th12}, %12;\n\t"
+            "mad.wide.u32 %12, tl12, %20, %12;\n\t"
+            "mov.b64 {tl13, th13}, %13;\n\t"
+            "mad.wide.u32 %13, tl13, %17, %13;\n\t"
+            "mov.b64 {tl14, th14}, %14;\n\t"
+            "mad.wide.u32 %14, tl14, %22, %14;\n\t"
+            "mov.b64 {tl15, th15}, %15;\n\t"
+            "mad.wide.u32 %15, tl15, %19, %15;\n\t"
+            "mov.b64 {tl0, th0}, %0;\n\t"
+            "mad.wide.u32 %0, tl0, %17, %0;\n\t"
+            "mov.b64 {tl1, th1}, %1;\n\t"
+            "mad.wide.u32 %1, tl1, %22, %1;\n\t"
+            "mov.b64 {tl2, th2}, %2;\n\t"
+            "mad.wide.u32 %2, tl2, %19, %2;\n\t"
+            "mov.b64 {tl3, th3}, %3;\n\t"
+            "mad.wide.u32 %3, tl3, %16, %3;\n\t"
+            "mov.b64 {tl4, th4}, %4;\n\t"
+            "mad.wide.u32 %4, tl4, %21, %4;\n\t"
+            "mov.b64 {tl5, th5}, %5;\n\t"
+            "mad.wide.u32 %5, tl5, %18, %5;\n\t"
+            "mov.b64 {tl6, th6}, %6;\n\t"
+            "mad.wide.u32 %6, tl6, %23, %6;\n\t"
+            "mov.b64 {tl7, th7}, %7;\n\t"
+            "mad.wide.u32 %7, tl7, %20, %7;\n\t"
+            "mov.b64 {tl8, th8}, %8;\n\t"
+            "mad.wide.u32 %8, tl8, %17, %8;\n\t"
+            "mov.b64 {tl9, th9}, %9;\n\t"
+            "mad.wide.u32 %9, tl9, %22, %9;\n\t"
+            "mov.b64 {tl10, th10}, %10;\n\t"
+            "mad.wide.u32 %10, tl10, %19, %10;\n\t"
+            "mov.b64 {tl11, th11}, %11;\n\t"
+            "mad.wide.u32 %11, tl11, %16, %11;\n\t"
+            "mov.b64 {tl12, th12}, %12;\n\t"
+            "mad.wide.u32 %12, tl12, %21, %12;\n\t"
+            "mov.b64 {tl13, th13}, %13;\n\t"
+            "mad.wide.u32 %13, tl13, %18, %13;\n\t"
+            "mov.b64 {tl14, th14}, %14;\n\t"
+            "mad.wide.u32 %14, tl14, %23, %14;\n\t"
+            "mov.b64 {tl15, th15}, %15;\n\t"
+            "mad.wide.u32 %15, tl15, %20, %15;\n\t"
+            "}"
+            : "+l"(c[0]), "+l"(c[1]), "+l"(c[2]), "+l"(c[3]), "+l"(c[4]), "+l"(c[5]), "+l"(c[6]), "+l"(c[7]), "+l"(c[8]), "+l"(c[9]), "+l"(c[10]), "+l"(c[11]), "+l"(c[12]), "+l"(c[13]), "+l"(c[14]), "+l"(c[15]) : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    }
+    uint64_t x = 0;
+    for (int i = 0; i < 16; i++) x ^= c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
+// every multiply takes the low word of its own accumulator as multiplicand, so nothing is loop invariant (reg)
+__global__ void k_asm_s32_rr(uint64_t* out, uint32_t a0, uint32_t b0, int iters) {
+    uint32_t b[8]; uint64_t c[16];
+    for (int i = 0; i < 8; i++) b[i] = (b0 * (i + 3) ^ blockIdx.x) | 1u;
+    for (int i = 0; i < 16; i++) c[i] = a0 * (i + 1) + threadIdx.x;
+    for (int k = 0; k < iters; k++) {
+        asm volatile("{\n\t.reg .b32 tl<16>, th<16>;\n\t"
+            "mov.b64 {tl0, th0}, %0;\n\t"
+            "mad.wide.s32 %0, tl0, %16, %0;\n\t"
+            "mov.b64 {tl1, th1}, %1;\n\t"
+            "mad.wide.s32 %1, tl1, %21, %1;\n\t"
+            "mov.b64 {tl2, th2}, %2;\n\t"
+            "mad.wide.s32 %2, tl2, %18, %2;\n\t"
+            "mov.b64 {tl3, th3}, %3;\n\t"
+            "mad.wide.s32 %3, tl3, %23, %3;\n\t"
+            "mov.b64 {tl4, th4}, %4;\n\t"
+            "mad.wide.s32 %4, tl4, %20, %4;\n\t"
+            "mov.b64 {tl5, th5}, %5;\n\t"
+            "mad.wide.s32 %5, tl5, %17, %5;\n\t"
+            "mov.b64 {tl6, th6}, %6;\n\t"
+            "mad.wide.s32 %6, tl6, %22, %6;\n\t"
+            "mov.b64 {tl7, th7}, %7;\n\t"
+            "mad.wide.s32 %7, tl7, %19, %7;\n\t"
+            "mov.b64 {tl8, th8}, %8;\n\t"
+            "mad.wide.s32 %8, tl8, %16, %8;\n\t"
+            "mov.b64 {tl9, th9}, %9;\n\t"
+            "mad.wide.s32 %9, tl9, %21, %9;\n\t"
+            "mov.b64 {tl10, th10}, %10;\n\t"
+            "mad.wide.s32 %10, tl10, %18, %10;\n\t"
+            "mov.b64 {tl11, th11}, %11;\n\t"
+            "mad.wide.s32 %11, tl11, %23, %11;\n\t"
+            "mov.b64 {tl12, th12}, %12;\n\t"
+            "mad.wide.s32 %12, tl12, %20, %12;\n\t"
+            "mov.b64 {tl13, th13}, %13;\n\t"
+            "mad.wide.s32 %13, tl13, %17, %13;\n\t"
+            "mov.b64 {tl14, th14}, %14;\n\t"
+            "mad.wide.s32 %14, tl14, %22, %14;\n\t"
+            "mov.b64 {tl15, th15}, %15;\n\t"
+            "mad.wide.s32 %15, tl15, %19, %15;\n\t"
+            "mov.b64 {tl0, th0}, %0;\n\t"
+            "mad.wide.s32 %0, tl0, %17, %0;\n\t"
+            "mov.b64 {tl1, th1}, %1;\n\t"
+            "mad.wide.s32 %1, tl1, %22, %1;\n\t"
+            "mov.b64 {tl2, th2}, %2;\n\t"
+            "mad.wide.s32 %2, tl2, %19, %2;\n\t"
+            "mov.b64 {tl3, th3}, %3;\n\t"
+            "mad.wide.s32 %3, tl3, %16, %3;\n\t"
+            "mov.b64 {tl4, th4}, %4;\n\t"
+            "mad.wide.s32 %4, tl4, %21, %4;\n\t"
+            "mov.b64 {tl5, th5}, %5;\n\t"
+            "mad.wide.s32 %5, tl5, %18, %5;\n\t"
+            "mov.b64 {tl6, th6}, %6;\n\t"
+            "mad.wide.s32 %6, tl6, %23, %6;\n\t"
+            "mov.b64 {tl7, th7}, %7;\n\t"
+            "mad.wide.s32 %7, tl7, %20, %7;\n\t"
+            "mov.b64 {tl8, th8}, %8;\n\t"
+            "mad.wide.s32 %8, tl8, %17, %8;\n\t"
+            "mov.b64 {tl9, th9}, %9;\n\t"
+            "mad.wide.s32 %9, tl9, %22, %9;\n\t"
+            "mov.b64 {tl10, th10}, %10;\n\t"
+            "mad.wide.s32 %10, tl10, %19, %10;\n\t"
+            "mov.b64 {tl11, th11}, %11;\n\t"
+            "mad.wide.s32 %11, tl11, %16, %11;\n\t"
+            "mov.b64 {tl12, th12}, %12;\n\t"
+            "mad.wide.s32 %12, tl12, %21, %12;\n\t"
+            "mov.b64 {tl13, th13}, %13;\n\t"
+            "mad.wide.s32 %13, tl13, %18, %13;\n\t"
+            "mov.b64 {tl14, th14}, %14;\n\t"
+            "mad.wide.s32 %14, tl14, %23, %14;\n\t"
+            "mov.b64 {tl15, th15}, %15;\n\t"
+            "mad.wide.s32 %15, tl15, %20, %15;\n\t"
+            "}"
+            : "+l"(c[0]), "+l"(c[1]), "+l"(c[2]), "+l"(c[3]), "+l"(c[4]), "+l"(c[5]), "+l"(c[6]), "+l"(c[7]), "+l"(c[8]), "+l"(c[9]), "+l"(c[10]), "+l"(c[11]), "+l"(c[12]), "+l"(c[13]), "+l"(c[14]), "+l"(c[15]) : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    }
+    uint64_t x = 0;
+    for (int i = 0; i < 16; i++) x ^= c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
+// every multiply takes the low word of its own accumulator as multiplicand, so nothing is loop invariant (imm)
+__global__ void k_asm_u32_ri(uint64_t* out, uint32_t a0, uint32_t b0, int iters) {
+    uint32_t b[8]; uint64_t c[16];
+    for (int i = 0; i < 8; i++) b[i] = (b0 * (i + 3) ^ blockIdx.x) | 1u;
+    for (int i = 0; i < 16; i++) c[i] = a0 * (i + 1) + threadIdx.x;
+    for (int k = 0; k < iters; k++) {
+        asm volatile("{\n\t.reg .b32 tl<16>, th<16>;\n\t"
+            "mov.b64 {tl0, th0}, %0;\n\t"
+            "mad.wide.u32 %0, tl0, 0x187cfd47, %0;\n\t"
+            "mov.b64 {tl1, th1}, %1;\n\t"
+            "mad.wide.u32 %1, tl1, 0x02db40c0, %1;\n\t"
+            "mov.b64 {tl2, th2}, %2;\n\t"
+            "mad.wide.u32 %2, tl2, 0x1c72a34f, %2;\n\t"
+            "mov.b64 {tl3, th3}, %3;\n\t"
+            "mad.wide.u32 %3, tl3, 0x0e5c2634, %3;\n\t"
+            "mov.b64 {tl4, th4}, %4;\n\t"
+            "mad.wide.u32 %4, tl4, 0x1585d978, %4;\n\t"
+            "mov.b64 {tl5, th5}, %5;\n\t"
+            "mad.wide.u32 %5, tl5, 0x010460b6, %5;\n\t"
+            "mov.b64 {tl6, th6}, %6;\n\t"
+            "mad.wide.u32 %6, tl6, 0x00a6e141, %6;\n\t"
+            "mov.b64 {tl7, th7}, %7;\n\t"
+            "mad.wide.u32 %7, tl7, 0x02d522d0, %7;\n\t"
+            "mov.b64 {tl8, th8}, %8;\n\t"
+            "mad.wide.u32 %8, tl8, 0x187cfd47, %8;\n\t"
+            "mov.b64 {tl9, th9}, %9;\n\t"
+            "mad.wide.u32 %9, tl9, 0x02db40c0, %9;\n\t"
+            "mov.b64 {tl10, th10}, %10;\n\t"
+            "mad.wide.u32 %10, tl10, 0x1c72a34f, %10;\n\t"
+            "mov.b64 {tl11, th11}, %11;\n\t"
+            "mad.wide.u32 %11, tl11, 0x0e5c2634, %11;\n\t"
+            "mov.b64 {tl12, th12}, %12;\n\t"
+            "mad.wide.u32 %12, tl12, 0x1585d978, %12;\n\t"
+            "mov.b64 {tl13, th13}, %13;\n\t"
+            "mad.wide.u32 %13, tl13, 0x010460b6, %13;\n\t"
+            "mov.b64 {tl14, th14}, %14;\n\t"
+            "mad.wide.u32 %14, tl14, 0x00a6e141, %14;\n\t"
+            "mov.b64 {tl15, th15}, %15;\n\t"
+            "mad.wide.u32 %15, tl15, 0x02d522d0, %15;\n\t"
+            "mov.b64 {tl0, th0}, %0;\n\t"
+            "mad.wide.u32 %0, tl0, 0x010460b6, %0;\n\t"
+            "mov.b64 {tl1, th1}, %1;\n\t"
+            "mad.wide.u32 %1, tl1, 0x00a6e141, %1;\n\t"
+            "mov.b64 {tl2, th2}, %2;\n\t"
+            "mad.wide.u32 %2, tl2, 0x02d522d0, %2;\n\t"
+            "mov.b64 {tl3, th3}, %3;\n\t"
+            "mad.wide.u32 %3, tl3, 0x187cfd47, %3;\n\t"
+            "mov.b64 {tl4, th4}, %4;\n\t"
+            "mad.wide.u32 %4, tl4, 0x02db40c0, %4;\n\t"
+            "mov.b64 {tl5, th5}, %5;\n\t"
+            "mad.wide.u32 %5, tl5, 0x1c72a34f, %5;\n\t"
+            "mov.b64 {tl6, th6}, %6;\n\t"
+            "mad.wide.u32 %6, tl6, 0x0e5c2634, %6;\n\t"
+            "mov.b64 {tl7, th7}, %7;\n\t"
+            "mad.wide.u32 %7, tl7, 0x1585d978, %7;\n\t"
+            "mov.b64 {tl8, th8}, %8;\n\t"
+            "mad.wide.u32 %8, tl8, 0x010460b6, %8;\n\t"
+            "mov.b64 {tl9, th9}, %9;\n\t"
+            "mad.wide.u32 %9, tl9, 0x00a6e141, %9;\n\t"
+            "mov.b64 {tl10, th10}, %10;\n\t"
+            "mad.wide.u32 %10, tl10, 0x02d522d0, %10;\n\t"
+            "mov.b64 {tl11, th11}, %11;\n\t"
+            "mad.wide.u32 %11, tl11, 0x187cfd47, %11;\n\t"
+            "mov.b64 {tl12, th12}, %12;\n\t"
+            "mad.wide.u32 %12, tl12, 0x02db40c0, %12;\n\t"
+            "mov.b64 {tl13, th13}, %13;\n\t"
+            "mad.wide.u32 %13, tl13, 0x1c72a34f, %13;\n\t"
+            "mov.b64 {tl14, th14}, %14;\n\t"
+            "mad.wide.u32 %14, tl14, 0x0e5c2634, %14;\n\t"
+            "mov.b64 {tl15, th15}, %15;\n\t"
+            "mad.wide.u32 %15, tl15, 0x1585d978, %15;\n\t"
+            "}"
+            : "+l"(c[0]), "+l"(c[1]), "+l"(c[2]), "+l"(c[3]), "+l"(c[4]), "+l"(c[5]), "+l"(c[6]), "+l"(c[7]), "+l"(c[8]), "+l"(c[9]), "+l"(c[10]), "+l"(c[11]), "+l"(c[12]), "+l"(c[13]), "+l"(c[14]), "+l"(c[15]) : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    }
+    uint64_t x = 0;
+    for (int i = 0; i < 16; i++) x ^= c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
 template <class F>
 static double time_ms(F launch) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -126,6 +449,17 @@ int main() {
     t = time_ms([&] { k_dfma<<<blocks, threads>>>((double*)buf, 1.000001, 0.999999, iters); });                  printf(", \"dfma_per_s\": %.4e", nthr * iters * 64 / (t * 1e-3));
     t = time_ms([&] { k_dfma_wide<<<blocks, threads>>>((double*)buf, 1.000001, 0.999999, 3, 5, iters); });       printf(", \"dfma_plus_wide_pairs_per_s\": %.4e", nthr * iters * 32 / (t * 1e-3));
     t = time_ms([&] { k_wide_alu<<<blocks, threads>>>((uint64_t*)buf, 0x9e3779b9u, 0x7f4a7c15u, iters); });      printf(", \"wide_plus_alu_pairs_per_s\": %.4e", nthr * iters * 32 / (t * 1e-3));
+    int it2 = 256;
+    t = time_ms([&] { k_swide_9x9<<<blocks, threads>>>((int64_t*)buf, 0x1234567, 0x7654321, it2); });   printf(", \"imad_wide_s32_9x9_per_s\": %.4e", nthr * it2 * 81 / (t * 1e-3));
+    t = time_ms([&] { k_uwide_9x9<<<blocks, threads>>>((uint64_t*)buf, 0x1234567, 0x7654321, it2); });  printf(", \"imad_wide_u32_9x9_per_s\": %.4e", nthr * it2 * 81 / (t * 1e-3));
+    t = time_ms([&] { k_uwide_imm<<<blocks, threads>>>((uint64_t*)buf, 0x1234567, it2); });             printf(", \"imad_wide_u32_imm_per_s\": %.4e", nthr * it2 * 64 / (t * 1e-3));
+    t = time_ms([&] { k_uwide_cbank<<<blocks, threads>>>((uint64_t*)buf, 0x1234567, it2); });           printf(", \"imad_wide_u32_cbank_per_s\": %.4e", nthr * it2 * 64 / (t * 1e-3));
+    t = time_ms([&] { k_uwide_regs<<<blocks, threads>>>((uint64_t*)buf, 0x1234567, it2); });            printf(", \"imad_wide_u32_regs_per_s\": %.4e", nthr * it2 * 64 / (t * 1e-3));
+    int blocks2 = sms * 4;   // 64+ registers per thread: 4 x 256 threads per SM
+    double nthr2 = (double)blocks2 * threads; int it3 = 4096;
+    t = time_ms([&] { k_asm_u32_rr<<<blocks2, threads>>>((uint64_t*)buf, 0x1234567, 0x7654321, it3); }); printf(", \"asm_mad_wide_u32_distinct_regs_per_s\": %.4e", nthr2 * it3 * 32 / (t * 1e-3));
+    t = time_ms([&] { k_asm_s32_rr<<<blocks2, threads>>>((uint64_t*)buf, 0x1234567, 0x7654321, it3); }); printf(", \"asm_mad_wide_s32_distinct_regs_per_s\": %.4e", nthr2 * it3 * 32 / (t * 1e-3));
+    t = time_ms([&] { k_asm_u32_ri<<<blocks2, threads>>>((uint64_t*)buf, 0x1234567, 0x7654321, it3); }); printf(", \"asm_mad_wide_u32_imm_per_s\": %.4e", nthr2 * it3 * 32 / (t * 1e-3));
     printf("}\n");
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
