@@ -1,5 +1,5 @@
-// BN254 arithmetic for the sm_100a verification kernels: Fp (fp29.cuh: 9 x 29-bit lazily reduced limbs,
-// carry-free IMAD.WIDE columns), the Fp2/Fp6/Fp12 tower, G1/G2 group law, optimal-ate line functions and
+// BN254 arithmetic for the sm_100a verification kernels: Fp (8 x 32-bit Montgomery limbs, PTX carry
+// chains from fp_ptx.cuh), the Fp2/Fp6/Fp12 tower, G1/G2 group law, optimal-ate line functions and
 // the final exponentiation.  This is the arithmetic the reference obtains from the EVM precompiles
 // ecAdd/ecMul/ecPairing (/root/reference/contracts/src/common/groth16.rs:12-14,54-55,121-125).
 //
@@ -14,7 +14,7 @@
 #define ZKV_INLINE __forceinline__
 #define ZKV_NOINLINE __noinline__
 #define ZKV_CONST static __device__ __constant__ const
-#define ZKV_TABLE static __device__ const          /* per-thread indexed tables: global memory through L1, not the constant bank */
+#define ZKV_TABLE static __device__ const          /* addressable per-thread operands: global memory through L1, not the constant bank */
 #else
 #define ZKV_HD
 #define ZKV_INLINE inline
@@ -23,141 +23,187 @@
 #define ZKV_TABLE static const
 #endif
 
-// Block-wide rendezvous.  The kernels are ~100 KB of straight-line code executed once per call site, i.e. pure streaming
+// Block-wide rendezvous.  The heavy kernels are ~150 KB of straight-line code executed once per call site, i.e. pure streaming
 // instruction fetch; warps of an SM that drift apart each need their own fetch stream and the kernels become
-// instruction-fetch bound (ncu: stall_no_instruction 3.9 per issue with 2 warps per scheduler).  All control flow of the
-// Fp6-and-above routines is input independent, so a barrier at their entry keeps the warps of a block on the same cache lines.
-// Only routines that EVERY thread of a block calls the same number of times may contain it (Fp2-level and curve
-// routines, which the data-dependent group-law code also uses, do not).
+// instruction-fetch bound (ncu: stall_no_instruction 3.9 per issue with 2 warps per scheduler, profiles/).  All control flow of
+// the Fp6-and-above routines is input independent, so a barrier at their entry keeps the warps of a block on the same cache lines.
+// Only routines that EVERY thread of a block calls the same number of times may contain it (Fp2-level and curve routines,
+// which the data-dependent group-law code also uses, do not).
+#ifndef ZKV_RDV_LEVEL
+#define ZKV_RDV_LEVEL 2
+#endif
 #if defined(__CUDA_ARCH__) && !defined(ZKV_NO_LOCKSTEP)
 #define ZKV_RENDEZVOUS() __syncthreads()
 #else
 #define ZKV_RENDEZVOUS()
 #endif
+#if ZKV_RDV_LEVEL >= 1
+#define ZKV_RENDEZVOUS1() ZKV_RENDEZVOUS()
+#else
+#define ZKV_RENDEZVOUS1()
+#endif
+#if ZKV_RDV_LEVEL >= 2
+#define ZKV_RENDEZVOUS2() ZKV_RENDEZVOUS()
+#else
+#define ZKV_RENDEZVOUS2()
+#endif
 
 #include "bn254_consts.cuh"
-#include "fp29.cuh"
+#if defined(__CUDACC__)
+#include "fp_ptx.cuh"
+#endif
 
 namespace zkv {
 
+struct alignas(16) fp { uint32_t v[8]; };
 struct fp2 { fp c0, c1; };
 struct fp6 { fp2 c0, c1, c2; };
 struct fp12 { fp6 c0, c1; };
 
+// ------------------------------------------------------------------------------------------ Fp
+ZKV_HD ZKV_INLINE fp fp_const(const uint32_t* c) { fp r; for (int i = 0; i < 8; i++) r.v[i] = c[i]; return r; }
+ZKV_HD ZKV_INLINE fp fp_zero() { fp r; for (int i = 0; i < 8; i++) r.v[i] = 0; return r; }
+ZKV_HD ZKV_INLINE fp fp_one() { return fp_const(C_ONE); }
+ZKV_HD ZKV_INLINE bool fp_is_zero(const fp& a) { uint32_t t = 0; for (int i = 0; i < 8; i++) t |= a.v[i]; return t == 0; }
+ZKV_HD ZKV_INLINE bool fp_eq(const fp& a, const fp& b) { uint32_t t = 0; for (int i = 0; i < 8; i++) t |= a.v[i] ^ b.v[i]; return t == 0; }
+// raw (non-Montgomery) 256-bit compare a >= m
+ZKV_HD ZKV_INLINE bool u256_geq(const uint32_t* a, const uint32_t* m) {
+    uint32_t borrow = 0;
+    for (int i = 0; i < 8; i++) { uint64_t t = (uint64_t)a[i] - m[i] - borrow; borrow = (uint32_t)(t >> 63); }
+    return borrow == 0;
+}
+
+#if defined(__CUDA_ARCH__)
+ZKV_HD ZKV_INLINE void fp_mul(fp& r, const fp& a, const fp& b) { fp_mul_ptx(r.v, a.v, b.v); }
+ZKV_HD ZKV_INLINE void fp_add(fp& r, const fp& a, const fp& b) { fp_add_ptx(r.v, a.v, b.v); }
+ZKV_HD ZKV_INLINE void fp_sub(fp& r, const fp& a, const fp& b) { fp_sub_ptx(r.v, a.v, b.v); }
+#else
+// portable backend (host emulation for tests only)
+ZKV_HD inline void fp_mul(fp& r, const fp& a, const fp& b) {
+    uint32_t t[10] = {0};
+    for (int i = 0; i < 8; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < 8; j++) { c += (uint64_t)a.v[j] * b.v[i] + t[j]; t[j] = (uint32_t)c; c >>= 32; }
+        c += t[8]; t[8] = (uint32_t)c; t[9] = (uint32_t)(c >> 32);
+        uint32_t m = t[0] * 0xe4866389u;
+        c = (uint64_t)m * C_P[0] + t[0]; c >>= 32;
+        for (int j = 1; j < 8; j++) { c += (uint64_t)m * C_P[j] + t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
+        c += t[8]; t[7] = (uint32_t)c; t[8] = t[9] + (uint32_t)(c >> 32);
+    }
+    if (t[8] || u256_geq(t, C_P)) { uint32_t bo = 0; for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)t[i] - C_P[i] - bo; r.v[i] = (uint32_t)d; bo = (uint32_t)(d >> 63); } }
+    else for (int i = 0; i < 8; i++) r.v[i] = t[i];
+}
+ZKV_HD inline void fp_add(fp& r, const fp& a, const fp& b) {
+    uint32_t t[8]; uint64_t c = 0;
+    for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + b.v[i]; t[i] = (uint32_t)c; c >>= 32; }
+    if (u256_geq(t, C_P)) { uint32_t bo = 0; for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)t[i] - C_P[i] - bo; r.v[i] = (uint32_t)d; bo = (uint32_t)(d >> 63); } }
+    else for (int i = 0; i < 8; i++) r.v[i] = t[i];
+}
+ZKV_HD inline void fp_sub(fp& r, const fp& a, const fp& b) {
+    uint32_t t[8]; uint32_t bo = 0;
+    for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)a.v[i] - b.v[i] - bo; t[i] = (uint32_t)d; bo = (uint32_t)(d >> 63); }
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) { c += (uint64_t)t[i] + (bo ? C_P[i] : 0); r.v[i] = (uint32_t)c; c >>= 32; }
+}
+#endif
+ZKV_HD ZKV_INLINE void fp_sqr(fp& r, const fp& a) { fp_mul(r, a, a); }
+ZKV_HD ZKV_INLINE void fp_dbl(fp& r, const fp& a) { fp_add(r, a, a); }
+ZKV_HD ZKV_INLINE void fp_neg(fp& r, const fp& a) { fp z = fp_zero(); fp_sub(r, z, a); }
+ZKV_HD ZKV_INLINE void fp_half(fp& r, const fp& a) {
+    uint32_t odd = 0u - (a.v[0] & 1u);
+    uint32_t t[8]; uint64_t c = 0;
+    for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + (C_P[i] & odd); t[i] = (uint32_t)c; c >>= 32; }
+    for (int i = 0; i < 7; i++) r.v[i] = (t[i] >> 1) | (t[i + 1] << 31);
+    r.v[7] = t[7] >> 1;   // a + p < 2^255: no carry out
+}
+ZKV_HD ZKV_INLINE void fp_to_mont(fp& r, const fp& a) { fp r2 = fp_const(C_R2); fp_mul(r, a, r2); }
+ZKV_HD ZKV_INLINE void fp_from_mont(fp& r, const fp& a) { fp one = fp_zero(); one.v[0] = 1; fp_mul(r, a, one); }
+// a^(p-2); inv(0) = 0
+ZKV_HD ZKV_NOINLINE void fp_inv(fp& r, const fp& a) {
+    fp acc = fp_one(), base = a;
+    for (int i = 253; i >= 0; i--) {
+        fp_sqr(acc, acc);
+        if ((C_PM2[i >> 5] >> (i & 31)) & 1) fp_mul(acc, acc, base);
+    }
+    r = acc;
+}
+
 // ------------------------------------------------------------------------------------------ Fp2 = Fp[u]/(u^2+1)
-// Bound conventions (checked by the ZKV_BOUNDS build): "N" = limbs 0..7 within 2^28 + small.  Every multiplication-type
-// routine returns N components; additions are lazy, so callers normalise (f2_norm) where a sum feeds a product whose
-// columns would otherwise overflow.
 ZKV_HD ZKV_INLINE fp2 f2_zero() { fp2 r; r.c0 = fp_zero(); r.c1 = fp_zero(); return r; }
 ZKV_HD ZKV_INLINE fp2 f2_one() { fp2 r; r.c0 = fp_one(); r.c1 = fp_zero(); return r; }
-ZKV_HD ZKV_INLINE fp2 f2_const(const int32_t c[2][9]) { fp2 r; r.c0 = fp_const(c[0]); r.c1 = fp_const(c[1]); return r; }
+ZKV_HD ZKV_INLINE fp2 f2_const(const uint32_t c[2][8]) { fp2 r; r.c0 = fp_const(c[0]); r.c1 = fp_const(c[1]); return r; }
 ZKV_HD ZKV_INLINE bool f2_is_zero(const fp2& a) { return fp_is_zero(a.c0) & fp_is_zero(a.c1); }
 ZKV_HD ZKV_INLINE bool f2_eq(const fp2& a, const fp2& b) { return fp_eq(a.c0, b.c0) & fp_eq(a.c1, b.c1); }
 ZKV_HD ZKV_INLINE void f2_add(fp2& r, const fp2& a, const fp2& b) { fp_add(r.c0, a.c0, b.c0); fp_add(r.c1, a.c1, b.c1); }
 ZKV_HD ZKV_INLINE void f2_sub(fp2& r, const fp2& a, const fp2& b) { fp_sub(r.c0, a.c0, b.c0); fp_sub(r.c1, a.c1, b.c1); }
 ZKV_HD ZKV_INLINE void f2_neg(fp2& r, const fp2& a) { fp_neg(r.c0, a.c0); fp_neg(r.c1, a.c1); }
 ZKV_HD ZKV_INLINE void f2_dbl(fp2& r, const fp2& a) { fp_dbl(r.c0, a.c0); fp_dbl(r.c1, a.c1); }
-ZKV_HD ZKV_INLINE void f2_norm(fp2& r, const fp2& a) { fp_norm(r.c0, a.c0); fp_norm(r.c1, a.c1); }
-ZKV_HD ZKV_INLINE void f2_normr(fp2& r, const fp2& a);
 ZKV_HD ZKV_INLINE void f2_half(fp2& r, const fp2& a) { fp_half(r.c0, a.c0); fp_half(r.c1, a.c1); }
 ZKV_HD ZKV_INLINE void f2_conj(fp2& r, const fp2& a) { r.c0 = a.c0; fp_neg(r.c1, a.c1); }
-// Lazily reduced product: the four limb products are accumulated in two column sets and only TWO Montgomery
-// reductions are done (c0 = a0 b0 - a1 b1, c1 = a0 b1 + a1 b0).  324 + 180 IMAD; no column subtractions.
 ZKV_HD ZKV_NOINLINE void f2_mul(fp2& r, const fp2& a, const fp2& b) {
-    cols c; fp r0;
-    fp_prod_set(c, a.c0, b.c0); fp_prod_sub(c, a.c1, b.c1); fp_redc(r0, c);
-    fp_prod_set(c, a.c0, b.c1); fp_prod_add(c, a.c1, b.c0); fp_redc(r.c1, c);
-    r.c0 = r0;
+    fp t0, t1, t2, s0, s1;
+    fp_mul(t0, a.c0, b.c0); fp_mul(t1, a.c1, b.c1);
+    fp_add(s0, a.c0, a.c1); fp_add(s1, b.c0, b.c1);
+    fp_mul(t2, s0, s1);
+    fp_sub(r.c0, t0, t1);
+    fp_sub(t2, t2, t0); fp_sub(r.c1, t2, t1);
 }
-// c0 = (a0 + a1)(a0 - a1), c1 = (2 a0) a1
 ZKV_HD ZKV_NOINLINE void f2_sqr(fp2& r, const fp2& a) {
-    fp s, d, r0; cols c;
-    fp_add(s, a.c0, a.c1); fp_sub(d, a.c0, a.c1);
-    fp_prod_set(c, s, d); fp_redc(r0, c);
-    fp_dbl(s, a.c0);
-    fp_prod_set(c, s, a.c1); fp_redc(r.c1, c);
-    r.c0 = r0;
+    fp s, d, m;
+    fp_add(s, a.c0, a.c1); fp_sub(d, a.c0, a.c1); fp_mul(m, a.c0, a.c1);
+    fp_mul(r.c0, s, d); fp_dbl(r.c1, m);
 }
 ZKV_HD ZKV_NOINLINE void f2_mul_fp(fp2& r, const fp2& a, const fp& k) { fp_mul(r.c0, a.c0, k); fp_mul(r.c1, a.c1, k); }
-// r = 9 a - b (sgn = -1) or 9 a + b (sgn = +1), carry-aware: 8a is formed as a whole-number shift so no limb overflows.
-// Output limbs: |r_i| < 2^29 + La + Lb + small.
-ZKV_HD ZKV_INLINE void fp_mul9_pm(fp& r, const fp& a, const fp& b, int sgn) {
-    int32_t lo[8], hi[8];
-    for (int i = 0; i < 8; i++) { lo[i] = (int32_t)((((uint32_t)a.v[i] << 3) + ZKV_LHALF) & ZKV_LMASK); hi[i] = (a.v[i] + (1 << 25)) >> 26; }   // 8 a_i = hi 2^29 + (lo - 2^28)
-    int32_t t8 = a.v[8] * 9 + hi[7] + (sgn < 0 ? -b.v[8] : b.v[8]);
-    int32_t t[8];
-    t[0] = lo[0] - ZKV_LHALF + a.v[0] + (sgn < 0 ? -b.v[0] : b.v[0]);
-    for (int i = 1; i < 8; i++) t[i] = lo[i] + (hi[i - 1] - ZKV_LHALF) + a.v[i] + (sgn < 0 ? -b.v[i] : b.v[i]);
-    for (int i = 0; i < 8; i++) r.v[i] = t[i];
-    r.v[8] = t8;
-    ZKV_B(r.L = ZKV_2P28 + a.L + b.L + std::ceil(a.L / 67108864.0) + 2; r.V = 9 * a.V + b.V;
-          if (r.L >= 8 * ZKV_2P28 - 64 || r.V > 500) zkv_bfail("fp_mul9_pm", r.L, r.V);)
+// (9+u)(a0 + a1 u) = (9 a0 - a1) + (9 a1 + a0) u
+ZKV_HD ZKV_NOINLINE void f2_mul_xi(fp2& r, const fp2& a) {
+    fp t0, t1;
+    fp_dbl(t0, a.c0); fp_dbl(t0, t0); fp_dbl(t0, t0); fp_add(t0, t0, a.c0);
+    fp_dbl(t1, a.c1); fp_dbl(t1, t1); fp_dbl(t1, t1); fp_add(t1, t1, a.c1);
+    fp n0, n1; fp_sub(n0, t0, a.c1); fp_add(n1, t1, a.c0);
+    r.c0 = n0; r.c1 = n1;
 }
-// Partial value reduction: subtract round-down(value / p) * p, estimated from the top limb (value / p ~ top / 3171406.3;
-// (top * 5) >> 24 ~ 0.945 value / p), with k p taken from a table.  Keeps |value| / p small after the x10 growth of a
-// multiplication by xi, which the Montgomery contraction (p / 2^261 ~ 1/170) alone cannot absorb.
-ZKV_HD ZKV_INLINE void fp_reduce_small(fp& r, const fp& a) {
-    ZKV_B(if (a.V > 67) zkv_bfail("fp_reduce_small", a.L, a.V);)
-    int32_t q = (a.v[8] * 5) >> 24;
-    const int32_t* row = C_KP[q + 64];
-    for (int i = 0; i < 9; i++) r.v[i] = a.v[i] - row[i];
-   
-    ZKV_B(r.L = a.L + ZKV_2P28; r.V = 0.055 * a.V + 1.01; if (r.L >= 8 * ZKV_2P28 - 64) zkv_bfail("fp_reduce_small limbs", r.L, r.V);)
-}
-// value reduction followed by a carry pass: for loop-carried results and wherever sums of products pile up
-ZKV_HD ZKV_INLINE void fp_normr(fp& r, const fp& a) { fp t; fp_reduce_small(t, a); fp_norm(r, t); }
-// (9+u)(a0 + a1 u) = (9 a0 - a1) + (9 a1 + a0) u; output limbs ~ 2^29 + 2^28 + 2 La, value reduced
-ZKV_HD ZKV_INLINE void f2_mul_xi(fp2& r, const fp2& a) {
-    fp n0, n1;
-    fp_mul9_pm(n0, a.c0, a.c1, -1); fp_mul9_pm(n1, a.c1, a.c0, +1);
-    fp_reduce_small(r.c0, n0); fp_reduce_small(r.c1, n1);
-}
-ZKV_HD ZKV_INLINE void f2_normr(fp2& r, const fp2& a) { fp_normr(r.c0, a.c0); fp_normr(r.c1, a.c1); }
 ZKV_HD ZKV_NOINLINE void f2_inv(fp2& r, const fp2& a) {
-    fp n, t; fp2 an; f2_norm(an, a);
-    fp_sqr(n, an.c0); fp_sqr(t, an.c1); fp_add(n, n, t); fp_inv(n, n);
-    fp_mul(r.c0, an.c0, n); fp_mul(t, an.c1, n); fp_neg(r.c1, t);
+    fp n, t;
+    fp_sqr(n, a.c0); fp_sqr(t, a.c1); fp_add(n, n, t); fp_inv(n, n);
+    fp_mul(r.c0, a.c0, n); fp_mul(t, a.c1, n); fp_neg(r.c1, t);
 }
 
 // ------------------------------------------------------------------------------------------ Fp6 = Fp2[v]/(v^3 - xi)
 ZKV_HD ZKV_INLINE void f6_add(fp6& r, const fp6& a, const fp6& b) { f2_add(r.c0, a.c0, b.c0); f2_add(r.c1, a.c1, b.c1); f2_add(r.c2, a.c2, b.c2); }
 ZKV_HD ZKV_INLINE void f6_sub(fp6& r, const fp6& a, const fp6& b) { f2_sub(r.c0, a.c0, b.c0); f2_sub(r.c1, a.c1, b.c1); f2_sub(r.c2, a.c2, b.c2); }
 ZKV_HD ZKV_INLINE void f6_neg(fp6& r, const fp6& a) { f2_neg(r.c0, a.c0); f2_neg(r.c1, a.c1); f2_neg(r.c2, a.c2); }
-ZKV_HD ZKV_INLINE void f6_norm(fp6& r, const fp6& a) { f2_norm(r.c0, a.c0); f2_norm(r.c1, a.c1); f2_norm(r.c2, a.c2); }
-ZKV_HD ZKV_INLINE void f6_normr(fp6& r, const fp6& a) { f2_normr(r.c0, a.c0); f2_normr(r.c1, a.c1); f2_normr(r.c2, a.c2); }
 ZKV_HD ZKV_INLINE void f6_mul_v(fp6& r, const fp6& a) { fp2 t; f2_mul_xi(t, a.c2); r.c2 = a.c1; r.c1 = a.c0; r.c0 = t; }
-// inputs N, output N
 ZKV_HD ZKV_NOINLINE void f6_mul(fp6& r, const fp6& a, const fp6& b) {
-    ZKV_RENDEZVOUS();
+    ZKV_RENDEZVOUS2();
     fp2 v0, v1, v2, t0, t1, t2, x0, x1;
     f2_mul(v0, a.c0, b.c0); f2_mul(v1, a.c1, b.c1); f2_mul(v2, a.c2, b.c2);
     f2_add(t0, a.c1, a.c2); f2_add(t1, b.c1, b.c2); f2_mul(t2, t0, t1);
-    f2_sub(t2, t2, v1); f2_sub(t2, t2, v2); f2_norm(t2, t2); f2_mul_xi(t2, t2); f2_add(x0, t2, v0);
+    f2_sub(t2, t2, v1); f2_sub(t2, t2, v2); f2_mul_xi(t2, t2); f2_add(x0, t2, v0);
     f2_add(t0, a.c0, a.c1); f2_add(t1, b.c0, b.c1); f2_mul(t2, t0, t1);
     f2_sub(t2, t2, v0); f2_sub(t2, t2, v1); f2_mul_xi(t0, v2); f2_add(x1, t2, t0);
     f2_add(t0, a.c0, a.c2); f2_add(t1, b.c0, b.c2); f2_mul(t2, t0, t1);
-    f2_sub(t2, t2, v0); f2_sub(t2, t2, v2); f2_add(t2, t2, v1);
-    f2_norm(r.c0, x0); f2_norm(r.c1, x1); f2_norm(r.c2, t2);
+    f2_sub(t2, t2, v0); f2_sub(t2, t2, v2); f2_add(r.c2, t2, v1);
+    r.c0 = x0; r.c1 = x1;
 }
-// a * (b0 + b1 v); inputs N, output N
+// a * (b0 + b1 v)
 ZKV_HD ZKV_NOINLINE void f6_mul_01(fp6& r, const fp6& a, const fp2& b0, const fp2& b1) {
-    ZKV_RENDEZVOUS();
+    ZKV_RENDEZVOUS2();
     fp2 v0, v1, t0, t1, t2, x0, x2;
     f2_mul(v0, a.c0, b0); f2_mul(v1, a.c1, b1);
     f2_mul(t2, a.c2, b1); f2_mul_xi(t2, t2); f2_add(x0, t2, v0);          // c0 = a0 b0 + xi a2 b1
     f2_mul(t2, a.c2, b0); f2_add(x2, t2, v1);                             // c2 = a1 b1 + a2 b0
     f2_add(t0, a.c0, a.c1); f2_add(t1, b0, b1); f2_mul(t2, t0, t1);       // c1 = (a0+a1)(b0+b1) - v0 - v1
-    f2_sub(t2, t2, v0); f2_sub(t2, t2, v1);
-    f2_norm(r.c0, x0); f2_norm(r.c1, t2); f2_norm(r.c2, x2);
+    f2_sub(t2, t2, v0); f2_sub(r.c1, t2, v1);
+    r.c0 = x0; r.c2 = x2;
 }
 ZKV_HD ZKV_NOINLINE void f6_inv(fp6& r, const fp6& a) {
-    ZKV_RENDEZVOUS();
+    ZKV_RENDEZVOUS2();
     fp2 A, B, C, t, F;
-    f2_sqr(A, a.c0); f2_mul(t, a.c1, a.c2); f2_mul_xi(t, t); f2_sub(A, A, t); f2_norm(A, A);
-    f2_sqr(B, a.c2); f2_mul_xi(B, B); f2_mul(t, a.c0, a.c1); f2_sub(B, B, t); f2_norm(B, B);
-    f2_sqr(C, a.c1); f2_mul(t, a.c0, a.c2); f2_sub(C, C, t); f2_norm(C, C);
+    f2_sqr(A, a.c0); f2_mul(t, a.c1, a.c2); f2_mul_xi(t, t); f2_sub(A, A, t);
+    f2_sqr(B, a.c2); f2_mul_xi(B, B); f2_mul(t, a.c0, a.c1); f2_sub(B, B, t);
+    f2_sqr(C, a.c1); f2_mul(t, a.c0, a.c2); f2_sub(C, C, t);
     f2_mul(F, a.c0, A);
-    f2_mul(t, a.c2, B); f2_mul_xi(t, t); f2_add(F, F, t); f2_norm(F, F);
+    f2_mul(t, a.c2, B); f2_mul_xi(t, t); f2_add(F, F, t);
     f2_mul(t, a.c1, C); f2_mul_xi(t, t); f2_add(F, F, t);
     f2_inv(F, F);
     f2_mul(r.c0, A, F); f2_mul(r.c1, B, F); f2_mul(r.c2, C, F);
@@ -168,54 +214,49 @@ ZKV_HD ZKV_INLINE fp12 f12_one() {
     fp12 r; fp2 z = f2_zero();
     r.c0.c0 = f2_one(); r.c0.c1 = z; r.c0.c2 = z; r.c1.c0 = z; r.c1.c1 = z; r.c1.c2 = z; return r;
 }
-ZKV_HD ZKV_INLINE void f12_canon(fp12& r, const fp12& a) {
-    const fp* w = &a.c0.c0.c0; fp* o = &r.c0.c0.c0;
-    for (int k = 0; k < 12; k++) fp_canon(o[k], w[k]);
-}
 ZKV_HD ZKV_INLINE bool f12_is_one(const fp12& a) {
-    fp one; { fp o = fp_one(); fp_canon(one, o); }
-    const fp* w = &a.c0.c0.c0; int32_t t = 0;
-    for (int k = 0; k < 12; k++) { fp c; fp_canon(c, w[k]); for (int i = 0; i < 9; i++) t |= k ? c.v[i] : (c.v[i] ^ one.v[i]); }
+    fp one = fp_one(); const fp* w = &a.c0.c0.c0; uint32_t t = 0;
+    for (int i = 0; i < 8; i++) t |= w[0].v[i] ^ one.v[i];
+    for (int k = 1; k < 12; k++) for (int i = 0; i < 8; i++) t |= w[k].v[i];
     return t == 0;
 }
-// inputs N, output N
 ZKV_HD ZKV_NOINLINE void f12_mul(fp12& r, const fp12& a, const fp12& b) {
     fp6 t0, t1, s0, s1, m;
     f6_mul(t0, a.c0, b.c0); f6_mul(t1, a.c1, b.c1);
-    f6_add(s0, a.c0, a.c1); f6_norm(s0, s0); f6_add(s1, b.c0, b.c1); f6_norm(s1, s1); f6_mul(m, s0, s1);
-    f6_sub(m, m, t0); f6_sub(m, m, t1); f6_normr(r.c1, m);
-    f6_mul_v(t1, t1); f6_add(t0, t0, t1); f6_normr(r.c0, t0);
+    f6_add(s0, a.c0, a.c1); f6_add(s1, b.c0, b.c1); f6_mul(m, s0, s1);
+    f6_sub(m, m, t0); f6_sub(r.c1, m, t1);
+    f6_mul_v(t1, t1); f6_add(r.c0, t0, t1);
 }
 // complex squaring: c0 = (a0+a1)(a0+v a1) - a0a1 - v a0a1 ; c1 = 2 a0a1
 ZKV_HD ZKV_NOINLINE void f12_sqr(fp12& r, const fp12& a) {
     fp6 ab, s0, s1, t;
     f6_mul(ab, a.c0, a.c1);
-    f6_add(s0, a.c0, a.c1); f6_norm(s0, s0); f6_mul_v(t, a.c1); f6_add(s1, a.c0, t); f6_norm(s1, s1);
+    f6_add(s0, a.c0, a.c1); f6_mul_v(t, a.c1); f6_add(s1, a.c0, t);
     f6_mul(s0, s0, s1);
-    f6_sub(s0, s0, ab); f6_mul_v(t, ab); f6_sub(s0, s0, t); f6_normr(r.c0, s0);
-    f6_add(t, ab, ab); f6_normr(r.c1, t);
+    f6_sub(s0, s0, ab); f6_mul_v(t, ab); f6_sub(r.c0, s0, t);
+    f6_add(r.c1, ab, ab);
 }
 ZKV_HD ZKV_INLINE void f12_conj(fp12& r, const fp12& a) { r.c0 = a.c0; f6_neg(r.c1, a.c1); }
 ZKV_HD ZKV_NOINLINE void f12_inv(fp12& r, const fp12& a) {
     fp6 t0, t1;
-    f6_mul(t0, a.c0, a.c0); f6_mul(t1, a.c1, a.c1); f6_mul_v(t1, t1); f6_sub(t0, t0, t1); f6_norm(t0, t0);
+    f6_mul(t0, a.c0, a.c0); f6_mul(t1, a.c1, a.c1); f6_mul_v(t1, t1); f6_sub(t0, t0, t1);
     f6_inv(t0, t0);
     f6_mul(r.c0, a.c0, t0); f6_mul(t1, a.c1, t0); f6_neg(r.c1, t1);
 }
-// f *= l0 + (l3 + l4 v) w      (sparse "034" line product, 13 Fp2 multiplications); f and the line N, result N
+// f *= l0 + (l3 + l4 v) w      (sparse "034" line product, 13 Fp2 multiplications)
 ZKV_HD ZKV_NOINLINE void f12_mul_line(fp12& f, const fp2& l0, const fp2& l3, const fp2& l4) {
-    ZKV_RENDEZVOUS();
+    ZKV_RENDEZVOUS1();
     fp6 t0, t1, s; fp2 l03;
     f2_mul(t0.c0, f.c0.c0, l0); f2_mul(t0.c1, f.c0.c1, l0); f2_mul(t0.c2, f.c0.c2, l0);
     f6_mul_01(t1, f.c1, l3, l4);
-    f6_add(s, f.c0, f.c1); f6_norm(s, s); f2_add(l03, l0, l3); f2_norm(l03, l03);
+    f6_add(s, f.c0, f.c1); f2_add(l03, l0, l3);
     f6_mul_01(s, s, l03, l4);
-    f6_sub(s, s, t0); f6_sub(s, s, t1); f6_normr(f.c1, s);
-    f6_mul_v(t1, t1); f6_add(t0, t0, t1); f6_normr(f.c0, t0);
+    f6_sub(s, s, t0); f6_sub(f.c1, s, t1);
+    f6_mul_v(t1, t1); f6_add(f.c0, t0, t1);
 }
-// f^(p^k), k in {1,2,3}; input N, output N
+// f^(p^k), k in {1,2,3}
 ZKV_HD ZKV_NOINLINE void f12_frob(fp12& r, const fp12& a, int k) {
-    ZKV_RENDEZVOUS();
+    ZKV_RENDEZVOUS1();
     fp2 c[6] = {a.c0.c0, a.c1.c0, a.c0.c1, a.c1.c1, a.c0.c2, a.c1.c2};   // coefficient of w^i
     for (int i = 0; i < 6; i++) {
         if (k & 1) f2_conj(c[i], c[i]);
@@ -226,33 +267,33 @@ ZKV_HD ZKV_NOINLINE void f12_frob(fp12& r, const fp12& a, int k) {
     }
     r.c0.c0 = c[0]; r.c1.c0 = c[1]; r.c0.c1 = c[2]; r.c1.c1 = c[3]; r.c0.c2 = c[4]; r.c1.c2 = c[5];
 }
-// one Fp4 squaring (a + b s)^2, s^2 = xi: t0 = a^2 + xi b^2, t1 = 2ab; a, b N
+// one Fp4 squaring (a + b s)^2, s^2 = xi: t0 = a^2 + xi b^2, t1 = 2ab
 ZKV_HD ZKV_INLINE void fp4_sqr(fp2& t0, fp2& t1, const fp2& a, const fp2& b) {
     fp2 a2, b2, s;
     f2_sqr(a2, a); f2_sqr(b2, b);
-    f2_add(s, a, b); f2_norm(s, s); f2_sqr(s, s); f2_sub(s, s, a2); f2_sub(t1, s, b2);
+    f2_add(s, a, b); f2_sqr(s, s); f2_sub(s, s, a2); f2_sub(t1, s, b2);
     f2_mul_xi(b2, b2); f2_add(t0, a2, b2);
 }
-// Granger-Scott squaring; valid only for elements of the cyclotomic subgroup; input N, output N
+// Granger-Scott squaring; valid only for elements of the cyclotomic subgroup
 ZKV_HD ZKV_NOINLINE void f12_cyc_sqr(fp12& r, const fp12& a) {
-    ZKV_RENDEZVOUS();
+    ZKV_RENDEZVOUS1();
     fp2 t0, t1, t2, t3, t4, t5, x;
     fp4_sqr(t0, t1, a.c0.c0, a.c1.c1);
     fp4_sqr(t2, t3, a.c1.c0, a.c0.c2);
     fp4_sqr(t4, t5, a.c0.c1, a.c1.c2);
-    f2_norm(t0, t0); f2_norm(t1, t1); f2_norm(t2, t2); f2_norm(t3, t3); f2_norm(t4, t4); f2_norm(t5, t5);
     fp2 z0 = a.c0.c0, z4 = a.c0.c1, z3 = a.c0.c2, z2 = a.c1.c0, z1 = a.c1.c1, z5 = a.c1.c2;
-    f2_sub(x, t0, z0); f2_dbl(x, x); f2_add(x, x, t0); f2_normr(r.c0.c0, x);     // 3 t0 - 2 z0
-    f2_add(x, t1, z1); f2_dbl(x, x); f2_add(x, x, t1); f2_normr(r.c1.c1, x);     // 3 t1 + 2 z1
-    f2_mul_xi(t5, t5); f2_norm(t5, t5);
-    f2_add(x, t5, z2); f2_dbl(x, x); f2_add(x, x, t5); f2_normr(r.c1.c0, x);     // 3 xi t5 + 2 z2
-    f2_sub(x, t4, z3); f2_dbl(x, x); f2_add(x, x, t4); f2_normr(r.c0.c2, x);     // 3 t4 - 2 z3
-    f2_sub(x, t2, z4); f2_dbl(x, x); f2_add(x, x, t2); f2_normr(r.c0.c1, x);     // 3 t2 - 2 z4
-    f2_add(x, t3, z5); f2_dbl(x, x); f2_add(x, x, t3); f2_normr(r.c1.c2, x);     // 3 t3 + 2 z5
+    f2_sub(x, t0, z0); f2_dbl(x, x); f2_add(r.c0.c0, x, t0);     // 3 t0 - 2 z0
+    f2_add(x, t1, z1); f2_dbl(x, x); f2_add(r.c1.c1, x, t1);     // 3 t1 + 2 z1
+    f2_mul_xi(t5, t5);
+    f2_add(x, t5, z2); f2_dbl(x, x); f2_add(r.c1.c0, x, t5);     // 3 xi t5 + 2 z2
+    f2_sub(x, t4, z3); f2_dbl(x, x); f2_add(r.c0.c2, x, t4);     // 3 t4 - 2 z3
+    f2_sub(x, t2, z4); f2_dbl(x, x); f2_add(r.c0.c1, x, t2);     // 3 t2 - 2 z4
+    f2_add(x, t3, z5); f2_dbl(x, x); f2_add(r.c1.c2, x, t3);     // 3 t3 + 2 z5
 }
 ZKV_HD ZKV_NOINLINE void f12_pow_u(fp12& r, const fp12& a) {   // a^u, a in the cyclotomic subgroup
     fp12 acc = a;
     for (int i = 61; i >= 0; i--) {
+        ZKV_RENDEZVOUS();
         f12_cyc_sqr(acc, acc);
         if ((ZKV_BN_U >> i) & 1) f12_mul(acc, acc, a);
     }
@@ -277,21 +318,21 @@ ZKV_HD ZKV_NOINLINE void final_exp(fp12& out, const fp12& m) {
 }
 
 // ------------------------------------------------------------------------------------------ G1: y^2 = x^3 + 3
-struct g1j { fp x, y, z; };            // Jacobian; z == 0 is infinity; coordinates N
+struct g1j { fp x, y, z; };            // Jacobian; z == 0 is infinity
 ZKV_HD ZKV_INLINE bool g1_on_curve(const fp& x, const fp& y) {
     fp l, r, three = fp_const(C_THREE); fp_sqr(l, y); fp_sqr(r, x); fp_mul(r, r, x); fp_add(r, r, three); return fp_eq(l, r);
 }
 ZKV_HD ZKV_NOINLINE void g1_dbl(g1j& r, const g1j& p) {   // infinity-safe: z=0 stays z=0
     fp A, B, C, D, E, F, t, x3, y3, z3;
     fp_sqr(A, p.x); fp_sqr(B, p.y); fp_sqr(C, B);
-    fp_add(t, p.x, B); fp_sqr(t, t); fp_sub(t, t, A); fp_sub(t, t, C); fp_dbl(D, t); fp_normr(D, D);
-    fp_dbl(E, A); fp_add(E, E, A); fp_norm(E, E); fp_sqr(F, E);
-    fp_dbl(t, D); fp_sub(x3, F, t); fp_normr(x3, x3);
-    fp_sub(t, D, x3); fp_mul(y3, E, t); fp_dbl(t, C); fp_dbl(t, t); fp_norm(t, t); fp_dbl(t, t); fp_sub(y3, y3, t); fp_normr(y3, y3);
-    fp_mul(z3, p.y, p.z); fp_dbl(z3, z3); fp_norm(z3, z3);
+    fp_add(t, p.x, B); fp_sqr(t, t); fp_sub(t, t, A); fp_sub(t, t, C); fp_dbl(D, t);
+    fp_dbl(E, A); fp_add(E, E, A); fp_sqr(F, E);
+    fp_dbl(t, D); fp_sub(x3, F, t);
+    fp_sub(t, D, x3); fp_mul(y3, E, t); fp_dbl(t, C); fp_dbl(t, t); fp_dbl(t, t); fp_sub(y3, y3, t);
+    fp_mul(z3, p.y, p.z); fp_dbl(z3, z3);
     r.x = x3; r.y = y3; r.z = z3;
 }
-// acc += (x2,y2) affine (N), complete (handles acc = inf, equal and opposite points)
+// acc += (x2,y2) affine, complete (handles acc = inf, equal and opposite points)
 ZKV_HD ZKV_NOINLINE void g1_add_affine(g1j& acc, const fp& x2, const fp& y2) {
     if (fp_is_zero(acc.z)) { acc.x = x2; acc.y = y2; acc.z = fp_one(); return; }
     fp z1z1, u2, s2, h, rr, hh, hhh, v, t, x3, y3;
@@ -302,30 +343,29 @@ ZKV_HD ZKV_NOINLINE void g1_add_affine(g1j& acc, const fp& x2, const fp& y2) {
         else { acc.x = fp_one(); acc.y = fp_one(); acc.z = fp_zero(); }
         return;
     }
-    fp_norm(h, h); fp_norm(rr, rr);
     fp_sqr(hh, h); fp_mul(hhh, hh, h); fp_mul(v, acc.x, hh);
-    fp_sqr(x3, rr); fp_sub(x3, x3, hhh); fp_dbl(t, v); fp_sub(x3, x3, t); fp_normr(x3, x3);
-    fp_sub(t, v, x3); fp_mul(y3, rr, t); fp_mul(t, acc.y, hhh); fp_sub(y3, y3, t); fp_normr(y3, y3);
+    fp_sqr(x3, rr); fp_sub(x3, x3, hhh); fp_dbl(t, v); fp_sub(x3, x3, t);
+    fp_sub(t, v, x3); fp_mul(y3, rr, t); fp_mul(t, acc.y, hhh); fp_sub(y3, y3, t);
     fp_mul(acc.z, acc.z, h); acc.x = x3; acc.y = y3;
 }
-ZKV_HD ZKV_INLINE bool g1_to_affine(fp& x, fp& y, const g1j& p) {   // returns false for infinity (x=y=0); x, y canonical
+ZKV_HD ZKV_INLINE bool g1_to_affine(fp& x, fp& y, const g1j& p) {   // returns false for infinity (x=y=0)
     if (fp_is_zero(p.z)) { x = fp_zero(); y = fp_zero(); return false; }
-    fp zi, zi2, t; fp_inv(zi, p.z); fp_sqr(zi2, zi); fp_mul(t, p.x, zi2); fp_canon(x, t); fp_mul(zi2, zi2, zi); fp_mul(t, p.y, zi2); fp_canon(y, t); return true;
+    fp zi, zi2; fp_inv(zi, p.z); fp_sqr(zi2, zi); fp_mul(x, p.x, zi2); fp_mul(zi2, zi2, zi); fp_mul(y, p.y, zi2); return true;
 }
 
 // ------------------------------------------------------------------------------------------ G2 on the twist y^2 = x^3 + 3/xi
-struct g2j { fp2 x, y, z; };           // Jacobian for the subgroup test; homogeneous projective in the Miller loop; coordinates N
+struct g2j { fp2 x, y, z; };           // Jacobian for the subgroup test; homogeneous projective in the Miller loop
 ZKV_HD ZKV_INLINE bool g2_on_curve(const fp2& x, const fp2& y) {
     fp2 l, r, b = f2_const(C_TWIST_B); f2_sqr(l, y); f2_sqr(r, x); f2_mul(r, r, x); f2_add(r, r, b); return f2_eq(l, r);
 }
 ZKV_HD ZKV_NOINLINE void g2_dbl(g2j& r, const g2j& p) {
     fp2 A, B, C, D, E, F, t, x3, y3, z3;
     f2_sqr(A, p.x); f2_sqr(B, p.y); f2_sqr(C, B);
-    f2_add(t, p.x, B); f2_norm(t, t); f2_sqr(t, t); f2_sub(t, t, A); f2_sub(t, t, C); f2_dbl(D, t); f2_normr(D, D);
-    f2_dbl(E, A); f2_add(E, E, A); f2_norm(E, E); f2_sqr(F, E);
-    f2_dbl(t, D); f2_sub(x3, F, t); f2_normr(x3, x3);
-    f2_sub(t, D, x3); f2_mul(y3, E, t); f2_dbl(t, C); f2_dbl(t, t); f2_norm(t, t); f2_dbl(t, t); f2_sub(y3, y3, t); f2_normr(y3, y3);
-    f2_mul(z3, p.y, p.z); f2_dbl(z3, z3); f2_norm(z3, z3);
+    f2_add(t, p.x, B); f2_sqr(t, t); f2_sub(t, t, A); f2_sub(t, t, C); f2_dbl(D, t);
+    f2_dbl(E, A); f2_add(E, E, A); f2_sqr(F, E);
+    f2_dbl(t, D); f2_sub(x3, F, t);
+    f2_sub(t, D, x3); f2_mul(y3, E, t); f2_dbl(t, C); f2_dbl(t, t); f2_dbl(t, t); f2_sub(y3, y3, t);
+    f2_mul(z3, p.y, p.z); f2_dbl(z3, z3);
     r.x = x3; r.y = y3; r.z = z3;
 }
 ZKV_HD ZKV_NOINLINE void g2_add(g2j& r, const g2j& p, const g2j& q) {   // complete
@@ -342,10 +382,9 @@ ZKV_HD ZKV_NOINLINE void g2_add(g2j& r, const g2j& p, const g2j& q) {   // compl
         else { r.x = f2_one(); r.y = f2_one(); r.z = f2_zero(); }
         return;
     }
-    f2_norm(h, h); f2_norm(rr, rr);
     f2_sqr(hh, h); f2_mul(hhh, hh, h); f2_mul(v, u1, hh);
-    f2_sqr(x3, rr); f2_sub(x3, x3, hhh); f2_dbl(t, v); f2_sub(x3, x3, t); f2_normr(x3, x3);
-    f2_sub(t, v, x3); f2_mul(y3, rr, t); f2_mul(t, s1, hhh); f2_sub(y3, y3, t); f2_normr(y3, y3);
+    f2_sqr(x3, rr); f2_sub(x3, x3, hhh); f2_dbl(t, v); f2_sub(x3, x3, t);
+    f2_sub(t, v, x3); f2_mul(y3, rr, t); f2_mul(t, s1, hhh); f2_sub(y3, y3, t);
     f2_mul(z3, p.z, q.z); f2_mul(z3, z3, h);
     r.x = x3; r.y = y3; r.z = z3;
 }
@@ -384,36 +423,35 @@ ZKV_HD ZKV_NOINLINE bool g2_in_subgroup(const fp2& qx, const fp2& qy) {
 
 // ------------------------------------------------------------------------------------------ Miller-loop steps
 // R in homogeneous projective coordinates (x = X/Z, y = Y/Z); a line is (l0,l3,l4) meaning
-// l0*yP + l3*xP*w + l4*v*w.  Formulas = oracle/bn254.h line_dbl/line_add (the shared convention).  R and the
-// line coefficients are kept N.
+// l0*yP + l3*xP*w + l4*v*w.  Formulas = oracle/bn254.h line_dbl/line_add (the shared convention).
 struct line_t { fp2 l0, l3, l4; };
 ZKV_HD ZKV_NOINLINE void line_dbl(g2j& R, line_t& l) {
-    ZKV_RENDEZVOUS();
+    ZKV_RENDEZVOUS2();
     fp2 A, B, C, E, F, G, H, J, E2, t, tb = f2_const(C_TWIST_B);
-    f2_mul(A, R.x, R.y); f2_half(A, A); f2_norm(A, A);
+    f2_mul(A, R.x, R.y); f2_half(A, A);
     f2_sqr(B, R.y); f2_sqr(C, R.z);
-    f2_dbl(t, C); f2_add(t, t, C); f2_norm(t, t); f2_mul(E, tb, t);
+    f2_dbl(t, C); f2_add(t, t, C); f2_mul(E, tb, t);
     f2_dbl(F, E); f2_add(F, F, E);
-    f2_add(G, B, F); f2_half(G, G); f2_norm(G, G);
-    f2_add(H, R.y, R.z); f2_norm(H, H); f2_sqr(H, H); f2_add(t, B, C); f2_sub(H, H, t); f2_norm(H, H);
-    f2_sub(t, E, B); f2_norm(l.l4, t);
+    f2_add(G, B, F); f2_half(G, G);
+    f2_add(H, R.y, R.z); f2_sqr(H, H); f2_add(t, B, C); f2_sub(H, H, t);
+    f2_sub(l.l4, E, B);
     f2_sqr(J, R.x);
     f2_sqr(E2, E);
-    f2_sub(t, B, F); f2_norm(t, t); f2_mul(R.x, A, t);
-    f2_sqr(G, G); f2_dbl(t, E2); f2_add(t, t, E2); f2_sub(t, G, t); f2_norm(R.y, t);
+    f2_sub(t, B, F); f2_mul(R.x, A, t);
+    f2_sqr(G, G); f2_dbl(t, E2); f2_add(t, t, E2); f2_sub(R.y, G, t);
     f2_mul(R.z, B, H);
-    f2_neg(l.l0, H); f2_dbl(t, J); f2_add(t, t, J); f2_norm(l.l3, t);
+    f2_neg(l.l0, H); f2_dbl(l.l3, J); f2_add(l.l3, l.l3, J);
 }
 ZKV_HD ZKV_NOINLINE void line_add(g2j& R, const fp2& qx, const fp2& qy, line_t& l) {
-    ZKV_RENDEZVOUS();
+    ZKV_RENDEZVOUS2();
     fp2 th, la, C, D, E, F, G, H, t, t2;
-    f2_mul(t, qy, R.z); f2_sub(t, R.y, t); f2_norm(th, t);
-    f2_mul(t, qx, R.z); f2_sub(t, R.x, t); f2_norm(la, t);
+    f2_mul(t, qy, R.z); f2_sub(th, R.y, t);
+    f2_mul(t, qx, R.z); f2_sub(la, R.x, t);
     f2_sqr(C, th); f2_sqr(D, la); f2_mul(E, la, D); f2_mul(F, R.z, C); f2_mul(G, R.x, D);
-    f2_add(H, E, F); f2_dbl(t, G); f2_sub(H, H, t); f2_norm(H, H);
-    f2_mul(t, th, qx); f2_mul(t2, la, qy); f2_sub(t, t, t2); f2_norm(l.l4, t);
+    f2_add(H, E, F); f2_dbl(t, G); f2_sub(H, H, t);
+    f2_mul(t, th, qx); f2_mul(t2, la, qy); f2_sub(l.l4, t, t2);
     l.l0 = la; f2_neg(l.l3, th);
-    f2_sub(t, G, H); f2_norm(t, t); f2_mul(t, th, t); f2_mul(t2, E, R.y); f2_sub(t, t, t2); f2_norm(R.y, t);
+    f2_sub(t, G, H); f2_mul(t, th, t); f2_mul(t2, E, R.y); f2_sub(R.y, t, t2);
     f2_mul(R.x, la, H);
     f2_mul(R.z, R.z, E);
 }
@@ -424,11 +462,14 @@ ZKV_HD ZKV_NOINLINE void g2_frob_affine(fp2& x, fp2& y, int k) {   // pi^k on af
     f2_mul(x, x, gx); f2_mul(y, y, gy);
 }
 // f *= line evaluated at the G1 point (px, py); with off != 0 the factor is replaced by 1 (a pair with a member at
-// infinity contributes 1, EIP-197) -- same instruction stream either way, so the block stays in lockstep
+// infinity contributes 1, EIP-197) by redirecting the operands to constants: l0 * py -> 1 * 1, l3 * px -> 0, l4 -> 0.
+// Same instruction stream either way, so the block stays in lockstep.
 ZKV_HD ZKV_INLINE void f12_mul_line_at(fp12& f, const line_t& l, const fp& px, const fp& py, bool off) {
-    fp2 a, b, c; f2_mul_fp(a, l.l0, py); f2_mul_fp(b, l.l3, px); c = l.l4;
-    if (off) { a = f2_one(); b = f2_zero(); c = f2_zero(); }
-    f12_mul_line(f, a, b, c);
+    const fp2* one2 = (const fp2*)C_ONE2; const fp2* zero2 = (const fp2*)C_ZERO2;
+    const fp2* l0 = off ? one2 : &l.l0; const fp2* l3 = off ? zero2 : &l.l3; const fp2* l4 = off ? zero2 : &l.l4;
+    const fp* y = off ? &one2->c0 : &py;
+    fp2 a, b; f2_mul_fp(a, *l0, *y); f2_mul_fp(b, *l3, px);
+    f12_mul_line(f, a, b, *l4);
 }
 // all ZKV_LINES_PER_G2 lines of a fixed G2 point, in the order the Miller loop consumes them
 ZKV_HD inline void g2_precompute_lines(line_t* out, const fp2& qx, const fp2& qy) {
@@ -446,36 +487,8 @@ ZKV_HD inline void g2_precompute_lines(line_t* out, const fp2& qx, const fp2& qy
 }
 
 // Multi-Miller loop: one variable G2 (qx,qy; pair 0) + nfixed tabled G2 points (pairs 1..nfixed).
-// skip bit j set => pair j contributes 1 (a member is infinity).  px/py: G1 points (Montgomery, affine, N).
+// skip bit j set => pair j contributes 1 (a member is infinity).  px/py: G1 points (Montgomery, affine).
 // Every thread executes every step (skipped pairs multiply by 1), so the control flow is uniform across a block.
-#if defined(ZKV_OLD_LOOP)
-ZKV_HD inline void miller_loop(fp12& f, const fp* px, const fp* py, const fp2& qx, const fp2& qy,
-                               const line_t* const* tabs, int nfixed, uint32_t skip) {
-    f = f12_one();
-    g2j R; R.x = qx; R.y = qy; R.z = f2_one();
-    line_t l; int li = 0;
-    const bool var_on = !(skip & 1u);
-    for (int d = ZKV_ATE_NAF_LEN - 2; d >= 0; d--) {
-        if (d != ZKV_ATE_NAF_LEN - 2) f12_sqr(f, f);
-        if (var_on) { line_dbl(R, l); f12_mul_line_at(f, l, px[0], py[0], false); }
-        for (int j = 0; j < nfixed; j++) if (!((skip >> (j + 1)) & 1u)) f12_mul_line_at(f, tabs[j][li], px[j + 1], py[j + 1], false);
-        li++;
-        int dg = C_ATE_NAF[d];
-        if (dg) {
-            if (var_on) { fp2 y = qy; if (dg < 0) f2_neg(y, y); line_add(R, qx, y, l); f12_mul_line_at(f, l, px[0], py[0], false); }
-            for (int j = 0; j < nfixed; j++) if (!((skip >> (j + 1)) & 1u)) f12_mul_line_at(f, tabs[j][li], px[j + 1], py[j + 1], false);
-            li++;
-        }
-    }
-    fp2 x1 = qx, y1 = qy; g2_frob_affine(x1, y1, 1);
-    fp2 x2 = qx, y2 = qy; g2_frob_affine(x2, y2, 2); f2_neg(y2, y2);
-    for (int s = 0; s < 2; s++) {
-        if (var_on) { line_add(R, s ? x2 : x1, s ? y2 : y1, l); f12_mul_line_at(f, l, px[0], py[0], false); }
-        for (int j = 0; j < nfixed; j++) if (!((skip >> (j + 1)) & 1u)) f12_mul_line_at(f, tabs[j][li], px[j + 1], py[j + 1], false);
-        li++;
-    }
-}
-#else
 ZKV_HD inline void miller_loop(fp12& f, const fp* px, const fp* py, const fp2& qx, const fp2& qy,
                                const line_t* const* tabs, int nfixed, uint32_t skip) {
     f = f12_one();
@@ -483,9 +496,9 @@ ZKV_HD inline void miller_loop(fp12& f, const fp* px, const fp* py, const fp2& q
     line_t l; int li = 0;
     const bool var_off = (skip & 1u) != 0;
     for (int d = ZKV_ATE_NAF_LEN - 2; d >= 0; d--) {
+        ZKV_RENDEZVOUS();
         if (d != ZKV_ATE_NAF_LEN - 2) f12_sqr(f, f);
-        line_dbl(R, l);
-        f12_mul_line_at(f, l, px[0], py[0], var_off);
+        line_dbl(R, l); f12_mul_line_at(f, l, px[0], py[0], var_off);
         for (int j = 0; j < nfixed; j++) f12_mul_line_at(f, tabs[j][li], px[j + 1], py[j + 1], ((skip >> (j + 1)) & 1u) != 0);
         li++;
         int dg = C_ATE_NAF[d];
@@ -495,34 +508,24 @@ ZKV_HD inline void miller_loop(fp12& f, const fp* px, const fp* py, const fp2& q
             for (int j = 0; j < nfixed; j++) f12_mul_line_at(f, tabs[j][li], px[j + 1], py[j + 1], ((skip >> (j + 1)) & 1u) != 0);
             li++;
         }
-#if defined(ZKV_TRACE)
-        printf("T d=%02d dg=%d li=%d f=%d %d %d R=%d %d\n", d, dg, li, f.c0.c0.c0.v[0], f.c1.c1.c0.v[4], f.c0.c2.c1.v[7], R.x.c0.v[0], R.y.c1.v[5]);
-#endif
     }
     fp2 x1 = qx, y1 = qy; g2_frob_affine(x1, y1, 1);
     fp2 x2 = qx, y2 = qy; g2_frob_affine(x2, y2, 2); f2_neg(y2, y2);
     for (int s = 0; s < 2; s++) {
-#if defined(ZKV_TRACE)
-        printf("T s=%d f=%d %d %d R=%d %d x1=%d y2=%d\n", s, f.c0.c0.c0.v[0], f.c1.c1.c0.v[4], f.c0.c2.c1.v[7], R.x.c0.v[0], R.y.c1.v[5], x1.c0.v[0], y2.c1.v[3]);
-#endif
         line_add(R, s ? x2 : x1, s ? y2 : y1, l); f12_mul_line_at(f, l, px[0], py[0], var_off);
         for (int j = 0; j < nfixed; j++) f12_mul_line_at(f, tabs[j][li], px[j + 1], py[j + 1], ((skip >> (j + 1)) & 1u) != 0);
         li++;
     }
 }
 
-#endif
-
 // ------------------------------------------------------------------------------------------ byte <-> field
-ZKV_HD ZKV_INLINE void be32_to_raw(uint32_t* v, const uint8_t* b) {   // 32-byte big-endian -> 8 LE 32-bit words (no reduction)
+ZKV_HD ZKV_INLINE void be32_to_raw(uint32_t* v, const uint8_t* b) {   // 32-byte big-endian -> 8 LE limbs (no reduction)
     for (int i = 0; i < 8; i++) { const uint8_t* q = b + 4 * (7 - i); v[i] = (uint32_t)q[0] << 24 | (uint32_t)q[1] << 16 | (uint32_t)q[2] << 8 | q[3]; }
 }
 ZKV_HD ZKV_INLINE void raw_to_be32(uint8_t* b, const uint32_t* v) {
     for (int i = 0; i < 8; i++) { uint8_t* q = b + 4 * (7 - i); q[0] = v[i] >> 24; q[1] = v[i] >> 16; q[2] = v[i] >> 8; q[3] = v[i]; }
 }
-// raw words (< p) -> Montgomery N
-ZKV_HD ZKV_INLINE void fp_from_raw_mont(fp& r, const uint32_t* w) { fp t; fp_from_words(t, w); fp_to_mont(r, t); }
-ZKV_HD ZKV_INLINE void fp_to_be32(uint8_t* b, const fp& a) { uint32_t w[8]; fp_from_mont_words(w, a); raw_to_be32(b, w); }
+ZKV_HD ZKV_INLINE void fp_to_be32(uint8_t* b, const fp& a) { fp t; fp_from_mont(t, a); raw_to_be32(b, t.v); }
 ZKV_HD inline void f12_to_bytes(uint8_t* out, const fp12& a) {   // 12 x BE-32, tower order c0.c0.c0, c0.c0.c1, c0.c1.c0, ...
     const fp* w = &a.c0.c0.c0;
     for (int i = 0; i < 12; i++) fp_to_be32(out + 32 * i, w[i]);

@@ -16,27 +16,33 @@ enum : uint8_t { ST_OK = 0, ST_INVALID_INITIALIZATION = 1, ST_INVALID_PROOF_DATA
 #define ZKV_WIN_PER_SCALAR 64          /* 256 / 4 */
 #define ZKV_WIN_ENTRIES 15             /* d = 1..15 */
 
-struct g1aff { fp x, y; };             // all-zero limbs encode infinity ((0,0) is not on the curve, so unambiguous)
-__device__ __forceinline__ bool limbs_all_zero(const fp& a) { int32_t t = 0; for (int i = 0; i < 9; i++) t |= a.v[i]; return t == 0; }
+struct g1aff { fp x, y; };             // (0,0) encodes infinity (not on the curve, so unambiguous)
 
 // ---------------------------------------------------------------------------- decode helpers
 // EIP-196 G1 decoding from raw limbs: returns 0 valid point (Montgomery x,y), 1 infinity, 2 invalid
 __device__ __forceinline__ int g1_decode_raw(fp& x, fp& y, const uint32_t* rx, const uint32_t* ry) {
-    if (u256_geq(rx, C_PW) || u256_geq(ry, C_PW)) return 2;
+    if (u256_geq(rx, C_P) || u256_geq(ry, C_P)) return 2;
     uint32_t any = 0;
     for (int i = 0; i < 8; i++) any |= rx[i] | ry[i];
     if (!any) { x = fp_zero(); y = fp_zero(); return 1; }
-    fp_from_raw_mont(x, rx);
-    fp_from_raw_mont(y, ry);
+    fp t;
+    for (int i = 0; i < 8; i++) t.v[i] = rx[i];
+    fp_to_mont(x, t);
+    for (int i = 0; i < 8; i++) t.v[i] = ry[i];
+    fp_to_mont(y, t);
     return g1_on_curve(x, y) ? 0 : 2;
 }
 // EIP-197 G2 decoding (wire order x_im, x_re, y_im, y_re), WITHOUT the subgroup test
 __device__ __forceinline__ int g2_decode_bytes(fp2& x, fp2& y, const uint8_t* b) {
     uint32_t r[4][8]; uint32_t any = 0; bool big = false;
-    for (int k = 0; k < 4; k++) { be32_to_raw(r[k], b + 32 * k); big |= u256_geq(r[k], C_PW); for (int i = 0; i < 8; i++) any |= r[k][i]; }
+    for (int k = 0; k < 4; k++) { be32_to_raw(r[k], b + 32 * k); big |= u256_geq(r[k], C_P); for (int i = 0; i < 8; i++) any |= r[k][i]; }
     if (big) return 2;
     if (!any) { x = f2_zero(); y = f2_zero(); return 1; }
-    fp_from_raw_mont(x.c1, r[0]); fp_from_raw_mont(x.c0, r[1]); fp_from_raw_mont(y.c1, r[2]); fp_from_raw_mont(y.c0, r[3]);
+    fp t;
+    for (int i = 0; i < 8; i++) t.v[i] = r[0][i]; fp_to_mont(x.c1, t);
+    for (int i = 0; i < 8; i++) t.v[i] = r[1][i]; fp_to_mont(x.c0, t);
+    for (int i = 0; i < 8; i++) t.v[i] = r[2][i]; fp_to_mont(y.c1, t);
+    for (int i = 0; i < 8; i++) t.v[i] = r[3][i]; fp_to_mont(y.c0, t);
     return g2_on_curve(x, y) ? 0 : 2;
 }
 
@@ -60,7 +66,7 @@ __global__ void k_decode(int n, const uint8_t* recs, size_t stride, size_t off, 
         for (int k = 0; k < 8; k++) any |= rx[k] | ry[k];
         if (any) {   // y = Q.wrapping_sub(y)  (mod 2^256)
             uint32_t bo = 0;
-            for (int k = 0; k < 8; k++) { uint64_t d = (uint64_t)C_PW[k] - ry[k] - bo; ry[k] = (uint32_t)d; bo = (uint32_t)(d >> 63); }
+            for (int k = 0; k < 8; k++) { uint64_t d = (uint64_t)C_P[k] - ry[k] - bo; ry[k] = (uint32_t)d; bo = (uint32_t)(d >> 63); }
         }
     }
     fp x, y;
@@ -107,7 +113,7 @@ __global__ void k_sp1_signals(int n, const uint8_t* vkeys, const uint8_t* pv, co
     uint32_t* o = scal + (size_t)i * 16;
     uint32_t s0[8];
     be32_to_raw(s0, vkeys + 32 * (size_t)i);
-    if (u256_geq(s0, C_RW)) flags[i] |= F_INVALID;
+    if (u256_geq(s0, C_R)) flags[i] |= F_INVALID;
     for (int k = 0; k < 8; k++) o[k] = s0[k];
     const uint8_t* msg; size_t len;
     if (pv_off) { msg = pv + pv_off[i]; len = (size_t)(pv_off[i + 1] - pv_off[i]); } else { msg = pv + (size_t)i * pv_stride; len = pv_stride; }
@@ -125,7 +131,7 @@ __global__ void k_generic_signals(int n, int k, const uint8_t* sig, uint32_t* sc
     for (int j = 0; j < k; j++) {
         uint32_t s[8];
         be32_to_raw(s, sig + ((size_t)i * k + j) * 32);
-        bad |= u256_geq(s, C_RW);
+        bad |= u256_geq(s, C_R);
         for (int t = 0; t < 8; t++) scal[((size_t)i * k + j) * 8 + t] = s[t];
     }
     if (bad) flags[i] |= F_INVALID;
@@ -137,7 +143,7 @@ __global__ void k_vkx(int n, const uint32_t* scal, int ns, int nwin, const g1aff
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g1j acc;
-    if (limbs_all_zero(base.x) && limbs_all_zero(base.y)) { acc.x = fp_one(); acc.y = fp_one(); acc.z = fp_zero(); }
+    if (fp_is_zero(base.x) && fp_is_zero(base.y)) { acc.x = fp_one(); acc.y = fp_one(); acc.z = fp_zero(); }
     else { acc.x = base.x; acc.y = base.y; acc.z = fp_one(); }
     for (int t = 0; t < ns; t++) {
         const uint32_t* s = scal + ((size_t)i * ns + t) * 8;
@@ -147,7 +153,7 @@ __global__ void k_vkx(int n, const uint32_t* scal, int ns, int nwin, const g1aff
             if (d) {
                 const g1aff* e = tt + w * ZKV_WIN_ENTRIES + (d - 1);
                 fp ex = e->x, ey = e->y;
-                if (!(limbs_all_zero(ex) && limbs_all_zero(ey))) g1_add_affine(acc, ex, ey);
+                if (!(fp_is_zero(ex) && fp_is_zero(ey))) g1_add_affine(acc, ex, ey);
             }
         }
     }
@@ -164,7 +170,7 @@ __global__ void k_g2_check(int n, const fp2* bx, const fp2* by, uint8_t* flags) 
     uint8_t fl = flags[i];
     if (fl & (F_INVALID | F_SELMIS)) return;
     fp2 x = bx[i], y = by[i];
-    if (limbs_all_zero(x.c0) && limbs_all_zero(x.c1) && limbs_all_zero(y.c0) && limbs_all_zero(y.c1)) return;      // infinity is a member
+    if (f2_is_zero(x) && f2_is_zero(y)) return;      // infinity is a member
     if (!g2_in_subgroup(x, y)) flags[i] = fl | F_INVALID;
 }
 
@@ -179,14 +185,14 @@ struct MillerArgs {
     uint8_t skip_bit[4];      // which flag bit disables pair j (0 = never)
     uint8_t vk_skip;          // pairs disabled for the whole batch (a vk G2 point at infinity)
 };
-// Launch shape of the two heavy kernels: ONE block per SM whose warps start together and run the same instruction
-// stream, so they share instruction-cache lines (two independent 128-thread blocks per SM drifted apart and
-// spent most of their time in instruction-fetch stalls: profiles/r1 notes).
+// Launch shape of the two heavy kernels: blocks whose warps start together, run the same instruction stream and meet at the
+// rendezvous points of bn254.cuh, so they share instruction-cache lines; two such blocks per SM run out of phase with each
+// other, which lets one block's integer-multiply bursts overlap the other's carry / load phases.
 #ifndef ZKV_HTPB
-#define ZKV_HTPB 256
+#define ZKV_HTPB 128
 #endif
 #ifndef ZKV_MINBLOCKS
-#define ZKV_MINBLOCKS 1
+#define ZKV_MINBLOCKS 2
 #endif
 __global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_miller(int n, MillerArgs a, const uint8_t* flags, fp12* out) {
     int i0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_final_exp(int n, co
     int i = i0 < n ? i0 : n - 1;
     uint8_t fl = flags[i];
     fp12 m = in[i], gt;
-    final_exp(gt, m);                                 // every thread runs it (k_miller left f = 1 for rejected inputs): uniform control flow
+    final_exp(gt, m);                                 // every thread runs it (k_miller left a harmless value for rejected inputs): uniform control flow
     if (i0 >= n) return;
     if (fl & (F_INVALID | F_SELMIS)) {
         status[i] = pairing_mode ? 2 : ((fl & F_SELMIS) ? ST_SELECTOR_MISMATCH : ST_VERIFICATION_FAILED);
@@ -315,10 +321,9 @@ __global__ void k_g1_decode4(int n, const uint8_t* g1s /* n x 4 x 64 */, const u
 __global__ void k_fp_mul_bytes(int n, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fp x, y, z; uint32_t w[8];
-    be32_to_raw(w, a + 32 * (size_t)i); fp_from_raw_mont(x, w);
-    be32_to_raw(w, b + 32 * (size_t)i); fp_from_raw_mont(y, w);
-    fp_mul(z, x, y);
+    fp x, y, z;
+    be32_to_raw(x.v, a + 32 * (size_t)i); be32_to_raw(y.v, b + 32 * (size_t)i);
+    fp_to_mont(x, x); fp_to_mont(y, y); fp_mul(z, x, y);
     fp_to_be32(out + 32 * (size_t)i, z);
 }
 __global__ void k_g2_check_bytes(int n, const uint8_t* g2s, uint8_t* out) {
@@ -418,7 +423,8 @@ __global__ void k_imad_wide(uint64_t* out, uint32_t a0, uint32_t b0, int iters) 
 // dependent chain of Montgomery multiplications per thread (throughput across many threads)
 __global__ void k_fpmul_chain(fp* out, int iters) {
     fp x = fp_one(), y = fp_const(C_R2);
-    x.v[0] ^= threadIdx.x & 0xff; y.v[1] ^= blockIdx.x & 0xff;
+    x.v[0] ^= threadIdx.x; y.v[1] ^= blockIdx.x;
+    x.v[7] &= 0x0fffffff; y.v[7] &= 0x0fffffff;
     for (int k = 0; k < iters; k++) { fp_mul(x, x, y); fp_mul(y, y, x); }
     fp_add(x, x, y);
     out[blockIdx.x * blockDim.x + threadIdx.x] = x;

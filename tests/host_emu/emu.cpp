@@ -1,11 +1,10 @@
 // TEST INFRASTRUCTURE: compiles csrc/bn254.cuh as plain C++ (portable Fp backend) so the tower / curve /
 // pairing logic the kernels use can be compared with the oracle on a CPU-only box.  Never shipped.
 #include <cstring>
-#include <cstdio>
 #include "../../stylus_zkvm_verifiers_b200/csrc/bn254.cuh"
 using namespace zkv;
 
-static bool dec_fp(fp& r, const uint8_t* b) { uint32_t w[8]; be32_to_raw(w, b); if (u256_geq(w, C_PW)) return false; fp_from_raw_mont(r, w); return true; }
+static bool dec_fp(fp& r, const uint8_t* b) { fp t; be32_to_raw(t.v, b); if (u256_geq(t.v, C_P)) return false; fp_to_mont(r, t); return true; }
 static bool dec_g2(fp2& x, fp2& y, const uint8_t* b) { return dec_fp(x.c1, b) && dec_fp(x.c0, b + 32) && dec_fp(y.c1, b + 64) && dec_fp(y.c0, b + 96); }
 static void dec_f12(fp12& a, const uint8_t* in) { fp* w = &a.c0.c0.c0; for (int i = 0; i < 12; i++) dec_fp(w[i], in + 32 * i); }
 

@@ -1,6 +1,6 @@
 """CPU-side check of the arithmetic the kernels are built from: csrc/bn254.cuh compiled as plain C++
-(tests/host_emu/emu.cpp) against the oracle, in two builds: as the kernels run it, and with the ZKV_BOUNDS shadow
-that proves the lazily reduced 29-bit-limb arithmetic of csrc/fp29.cuh cannot overflow."""
+(tests/host_emu/emu.cpp) against the oracle, and the PTX instruction lists of csrc/fp_ptx.cuh simulated
+against Python integers (tools/gen_fp_ptx.py --check)."""
 import ctypes as C
 import os
 import subprocess
@@ -18,22 +18,30 @@ w32 = O.w32
 G1 = w32(1) + w32(2)
 
 
-@pytest.fixture(scope="module", params=["plain", "bounds"])
-def emu(request):
-    """plain: the arithmetic exactly as the kernels run it.  bounds: same code with the ZKV_BOUNDS shadow (fp29.cuh) that
-    aborts on any limb / column / value bound violation -- control flow is input independent, so a passing run proves
-    the lazy reduction never overflows for ANY input."""
+@pytest.fixture(scope="module")
+def emu():
     d = os.path.join(ROOT, "tests", "host_emu")
-    bounds = request.param == "bounds"
-    so = os.path.join(d, "libzkv_emu_bounds.so" if bounds else "libzkv_emu.so")
-    srcs = [os.path.join(d, "emu.cpp")] + [os.path.join(ROOT, "stylus_zkvm_verifiers_b200", "csrc", f) for f in ("bn254.cuh", "bn254_consts.cuh", "fp29.cuh")]
+    so = os.path.join(d, "libzkv_emu.so")
+    srcs = [os.path.join(d, "emu.cpp")] + [os.path.join(ROOT, "stylus_zkvm_verifiers_b200", "csrc", f) for f in ("bn254.cuh", "bn254_consts.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC"] + (["-DZKV_BOUNDS"] if bounds else []) + ["-o", so, srcs[0]])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, srcs[0]])
     return C.CDLL(so)
 
 
 def rand_f12(rng):
     return b"".join(w32(rng.u256() % P) for _ in range(12))
+
+
+def test_ptx_instruction_lists_simulate_correctly():
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_fp_ptx.py"), "--check"])
+
+
+def test_generated_header_is_current():
+    """csrc/fp_ptx.cuh must be exactly what the (verified) generator emits."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_fp_ptx", os.path.join(ROOT, "tools", "gen_fp_ptx.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    assert open(os.path.join(ROOT, "stylus_zkvm_verifiers_b200", "csrc", "fp_ptx.cuh")).read() == g.render()
 
 
 def test_fp_and_fp12_ops(emu):
