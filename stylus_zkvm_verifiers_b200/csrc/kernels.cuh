@@ -406,19 +406,25 @@ __global__ void k_g2_mul(int n, const uint8_t* pts /* n x 128 or 1 x 128 if bcas
 }
 
 // ---------------------------------------------------------------------------- K0: integer-pipe microbenchmarks
-// 8 independent 64-bit accumulators per thread, each updated by IMAD.WIDE.U32 (mad.wide.u32)
-__global__ void k_imad_wide(uint64_t* out, uint32_t a0, uint32_t b0, int iters) {
-    uint32_t a = a0 + threadIdx.x, b = b0 ^ blockIdx.x;
-    uint64_t c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8;
+// IMAD.WIDE.U32 issue rate: two 8-limb accumulators per thread, each row = a 4-product mad.lo.cc / madc.hi.cc chain (the
+// instruction mix of one multiplier row).  The carry flags make every product loop-variant, so ptxas can neither hoist the
+// multiplies out of the loop nor split them into IMAD + IADD (a plain `c += a * b` microbenchmark is silently reduced to
+// 64-bit adds).  64 IMAD.WIDE per loop iteration.
+__global__ void k_imad_wide(uint32_t* out, uint32_t a0, uint32_t b0, int iters) {
+    uint32_t a1 = a0 + threadIdx.x, a2 = a1 * 3, a3 = a1 * 5, a4 = a1 * 7, b = b0 ^ blockIdx.x;
+    uint32_t e0 = 1, e1 = 2, e2 = 3, e3 = 4, e4 = 5, e5 = 6, e6 = 7, e7 = 8, o0 = 9, o1 = 10, o2 = 11, o3 = 12, o4 = 13, o5 = 14, o6 = 15, o7 = 16;
     for (int k = 0; k < iters; k++) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            asm volatile("mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\tmad.wide.u32 %2, %8, %9, %2;\n\tmad.wide.u32 %3, %8, %9, %3;\n\t"
-                         "mad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\tmad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
-                         : "+l"(c0), "+l"(c1), "+l"(c2), "+l"(c3), "+l"(c4), "+l"(c5), "+l"(c6), "+l"(c7) : "r"(a), "r"(b));
+            asm volatile("mad.lo.cc.u32 %0, %16, %20, %0;\n\tmadc.hi.cc.u32 %1, %16, %20, %1;\n\tmadc.lo.cc.u32 %2, %17, %20, %2;\n\tmadc.hi.cc.u32 %3, %17, %20, %3;\n\t"
+                         "madc.lo.cc.u32 %4, %18, %20, %4;\n\tmadc.hi.cc.u32 %5, %18, %20, %5;\n\tmadc.lo.cc.u32 %6, %19, %20, %6;\n\tmadc.hi.u32 %7, %19, %20, %7;\n\t"
+                         "mad.lo.cc.u32 %8, %17, %20, %8;\n\tmadc.hi.cc.u32 %9, %17, %20, %9;\n\tmadc.lo.cc.u32 %10, %18, %20, %10;\n\tmadc.hi.cc.u32 %11, %18, %20, %11;\n\t"
+                         "madc.lo.cc.u32 %12, %19, %20, %12;\n\tmadc.hi.cc.u32 %13, %19, %20, %13;\n\tmadc.lo.cc.u32 %14, %16, %20, %14;\n\tmadc.hi.u32 %15, %16, %20, %15;"
+                         : "+r"(e0), "+r"(e1), "+r"(e2), "+r"(e3), "+r"(e4), "+r"(e5), "+r"(e6), "+r"(e7), "+r"(o0), "+r"(o1), "+r"(o2), "+r"(o3), "+r"(o4), "+r"(o5), "+r"(o6), "+r"(o7)
+                         : "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(b));
         }
     }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = e0 ^ e1 ^ e2 ^ e3 ^ e4 ^ e5 ^ e6 ^ e7 ^ o0 ^ o1 ^ o2 ^ o3 ^ o4 ^ o5 ^ o6 ^ o7;
 }
 // dependent chain of Montgomery multiplications per thread (throughput across many threads)
 __global__ void k_fpmul_chain(fp* out, int iters) {

@@ -675,7 +675,7 @@ extern "C" int zkv_imad_peak(int device, double* wide_per_s, double* fpmul_per_s
     float best_w = 1e30f, best_f = 1e30f;
     const int it_w = 4096, it_f = 2048;
     for (int rep = 0; rep < 5; rep++) {
-        CK(cudaEventRecord(e0)); k_imad_wide<<<blocks, threads>>>(d_out, 0x9e3779b9u, 0x7f4a7c15u, it_w); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        CK(cudaEventRecord(e0)); k_imad_wide<<<blocks, threads>>>((uint32_t*)d_out, 0x9e3779b9u, 0x7f4a7c15u, it_w); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep) best_w = std::min(best_w, ms);
         CK(cudaEventRecord(e0)); k_fpmul_chain<<<blocks, threads>>>(d_fp, it_f); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
         CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep) best_f = std::min(best_f, ms);
