@@ -140,6 +140,15 @@ ZKV_HD ZKV_INLINE void f2_neg(fp2& r, const fp2& a) { fp_neg(r.c0, a.c0); fp_neg
 ZKV_HD ZKV_INLINE void f2_dbl(fp2& r, const fp2& a) { fp_dbl(r.c0, a.c0); fp_dbl(r.c1, a.c1); }
 ZKV_HD ZKV_INLINE void f2_half(fp2& r, const fp2& a) { fp_half(r.c0, a.c0); fp_half(r.c1, a.c1); }
 ZKV_HD ZKV_INLINE void f2_conj(fp2& r, const fp2& a) { r.c0 = a.c0; fp_neg(r.c1, a.c1); }
+#if defined(__CUDA_ARCH__)
+// Lazily reduced (fp_ptx.cuh): the Karatsuba products stay 512 bits wide and only the two result coefficients are reduced.
+ZKV_HD ZKV_NOINLINE void f2_mul(fp2& r, const fp2& a, const fp2& b) {
+    fp2 t; fp2_mul_ptx(t.c0.v, t.c1.v, a.c0.v, a.c1.v, b.c0.v, b.c1.v); r = t;
+}
+ZKV_HD ZKV_NOINLINE void f2_sqr(fp2& r, const fp2& a) {
+    fp2 t; fp2_sqr_ptx(t.c0.v, t.c1.v, a.c0.v, a.c1.v); r = t;
+}
+#else
 ZKV_HD ZKV_NOINLINE void f2_mul(fp2& r, const fp2& a, const fp2& b) {
     fp t0, t1, t2, s0, s1;
     fp_mul(t0, a.c0, b.c0); fp_mul(t1, a.c1, b.c1);
@@ -153,6 +162,7 @@ ZKV_HD ZKV_NOINLINE void f2_sqr(fp2& r, const fp2& a) {
     fp_add(s, a.c0, a.c1); fp_sub(d, a.c0, a.c1); fp_mul(m, a.c0, a.c1);
     fp_mul(r.c0, s, d); fp_dbl(r.c1, m);
 }
+#endif
 ZKV_HD ZKV_NOINLINE void f2_mul_fp(fp2& r, const fp2& a, const fp& k) { fp_mul(r.c0, a.c0, k); fp_mul(r.c1, a.c1, k); }
 // (9+u)(a0 + a1 u) = (9 a0 - a1) + (9 a1 + a0) u
 ZKV_HD ZKV_NOINLINE void f2_mul_xi(fp2& r, const fp2& a) {

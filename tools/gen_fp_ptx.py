@@ -140,10 +140,10 @@ def final_sub(p, r, outs, bound2p=True):
         p.emit("selp_eqz", outs[k], s[k], r[k], bor)
 
 
-def reduce_row(p, E, O):
+def reduce_row(p, E, O, carry_in=False):
     m = p.op("mul.lo", E[0], M0)
     for idx, j in enumerate((1, 3, 5, 7)):
-        O[j - 1] = p.op("mad.lo.cc" if idx == 0 else "madc.lo.cc", m, PL[j], O[j - 1])
+        O[j - 1] = p.op("mad.lo.cc" if (idx == 0 and not carry_in) else "madc.lo.cc", m, PL[j], O[j - 1])
         O[j] = p.op("madc.hi.cc", m, PL[j], O[j])
     p.emit("assert_nc", None)
     for idx, j in enumerate((0, 2, 4, 6)):
@@ -209,6 +209,114 @@ def gen_sub():
     return p
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Lazily reduced Fp2 arithmetic (Aranha et al., "Faster explicit formulas for computing pairings over ordinary curves",
+# section 3): the three Karatsuba products of an Fp2 multiplication stay 512 bits wide, are combined there, and only the two
+# result coefficients go through a Montgomery reduction: 3 x 64 + 2 x 72 = 336 IMAD.WIDE instead of 3 x 136 = 408.
+def mul_wide(p, a, b):
+    """16-limb product of two 8-limb operands (no reduction), 64 IMAD.WIDE; same even/odd accumulator framing as gen_mul."""
+    out = []
+    E, O = [None] * N, [None] * N
+    for j in (0, 2, 4, 6):
+        E[j] = p.op("mul.lo", a[j], b[0]); E[j + 1] = p.op("mul.hi", a[j], b[0])
+    for j in (1, 3, 5, 7):
+        O[j - 1] = p.op("mul.lo", a[j], b[0]); O[j] = p.op("mul.hi", a[j], b[0])
+    out.append(E[0])
+    for i in range(1, N):
+        X = E[1]
+        Oin = E[2:] + [0, 0]
+        E = O
+        O = [None] * N
+        E[0] = p.op("add.cc", E[0], X)
+        for j in (1, 3, 5, 7):
+            O[j - 1] = p.op("madc.lo.cc", a[j], b[i], Oin[j - 1])
+            O[j] = p.op("madc.hi.cc", a[j], b[i], Oin[j])
+        p.emit("assert_nc", None)
+        for idx, j in enumerate((0, 2, 4, 6)):
+            E[j] = p.op("mad.lo.cc" if idx == 0 else "madc.lo.cc", a[j], b[i], E[j])
+            E[j + 1] = p.op("madc.hi.cc", a[j], b[i], E[j + 1])
+        O[7] = p.op("addc.cc", O[7], 0)
+        p.emit("assert_nc", None)
+        out.append(E[0])
+    out.append(p.op("add.cc", E[1], O[0]))
+    for k in range(1, 7):
+        out.append(p.op("addc.cc", E[k + 1], O[k]))
+    out.append(p.op("addc.cc", O[7], 0))
+    p.emit("assert_nc", None)
+    return out
+
+
+def redc_wide(p, T, outs):
+    """outs = T / 2^256 mod P, fully reduced, for a 16-limb T < P * 2^256: 72 IMAD.WIDE."""
+    E, O = list(T[:N]), [0] * N
+    for i in range(N):
+        reduce_row(p, E, O, carry_in=(i > 0))
+        if i < N - 1:
+            X = E[1]
+            Oin = E[2:] + [0, 0]
+            E = O
+            O = Oin
+            E[0] = p.op("add.cc", E[0], X)        # carry consumed by the first madc of the next reduce_row
+    u = [p.op("add.cc", E[1], O[0])]
+    for k in range(1, 7):
+        u.append(p.op("addc.cc", E[k + 1], O[k]))
+    u.append(p.op("addc.cc", O[7], 0))
+    p.emit("assert_nc", None)
+    r = [p.op("add.cc" if k == 0 else "addc.cc", u[k], T[N + k]) for k in range(N)]
+    p.emit("assert_nc", None)
+    final_sub(p, r, outs)
+
+
+def add_raw(p, a, b, n=N):
+    r = [p.op("add.cc" if k == 0 else "addc.cc", a[k], b[k]) for k in range(n)]
+    p.emit("assert_nc", None)
+    return r
+
+
+def sub_mod(p, a, b):
+    d = [p.op("sub.cc" if k == 0 else "subc.cc", a[k], b[k]) for k in range(N)]
+    bor = p.op("subc", 0, 0)
+    pm = [p.op("and", bor, PL[k]) for k in range(N)]
+    return [p.op("add.cc" if k == 0 else ("addc.cc" if k < 7 else "addc"), d[k], pm[k]) for k in range(N)]
+
+
+def gen_fp2_mul():
+    """(r, q) = (x + y u)(z + w u) in Fp[u]/(u^2+1):  r = xz - yw,  q = (x+y)(z+w) - xz - yw."""
+    nm = lambda c: ["%s%d" % (c, i) for i in range(N)]
+    x, y, z, w = nm("x"), nm("y"), nm("z"), nm("w")
+    p = Prog("fp2_mul", x + y + z + w, nm("r") + nm("q"))
+    s = add_raw(p, x, y)                    # < 2P < 2^255
+    t = add_raw(p, z, w)
+    T0 = mul_wide(p, x, z)
+    T1 = mul_wide(p, y, w)
+    T2 = mul_wide(p, s, t)                  # < 4 P^2 < 2^510; issued before the carry work on T0/T1 so that ptxas can run that work in the
+                                            # shadow of these multiplies (IMAD.WIDE issues every 4th cycle, the ALU chains fill the gaps)
+    # C0 = T0 - T1 (+ P * 2^256 if negative)  in [0, P * 2^256)
+    d = [p.op("sub.cc" if k == 0 else "subc.cc", T0[k], T1[k]) for k in range(2 * N)]
+    bor = p.op("subc", 0, 0)
+    pm = [p.op("and", bor, PL[k]) for k in range(N)]
+    C0 = d[:N] + [p.op("add.cc" if k == 0 else ("addc.cc" if k < 7 else "addc"), d[N + k], pm[k]) for k in range(N)]
+    S = add_raw(p, T0, T1, 2 * N)           # < 2 P^2
+    C1 = [p.op("sub.cc" if k == 0 else "subc.cc", T2[k], S[k]) for k in range(2 * N)]
+    p.emit("assert_nc", None)               # xw + yz >= 0
+    redc_wide(p, C0, nm("r"))
+    redc_wide(p, C1, nm("q"))
+    return p
+
+
+def gen_fp2_sqr():
+    """(r, q) = (x + y u)^2:  r = (x+y)(x-y),  q = (2x) y.  Operands of the two products are < 2P, so the unreduced sum / double is enough."""
+    nm = lambda c: ["%s%d" % (c, i) for i in range(N)]
+    x, y = nm("x"), nm("y")
+    p = Prog("fp2_sqr", x + y, nm("r") + nm("q"))
+    s = add_raw(p, x, y)
+    d = sub_mod(p, x, y)
+    m = add_raw(p, x, x)
+    redc_wide(p, mul_wide(p, s, d), nm("r"))
+    redc_wide(p, mul_wide(p, m, y), nm("q"))
+    return p
+
+
 def limbs(x):
     return [(x >> (32 * i)) & MASK for i in range(N)]
 
@@ -229,7 +337,29 @@ def check(verbose=True, iters=3000):
         assert unl(mul.run(inp)) == x * y * rinv % P, ("mul", hex(x), hex(y))
         assert unl(add.run(inp)) == (x + y) % P, ("add", hex(x), hex(y))
         assert unl(sub.run(inp)) == (x - y) % P, ("sub", hex(x), hex(y))
+    f2m, f2s = gen_fp2_mul(), gen_fp2_sqr()
+    top = (1 << 256) - 1
+    cases2 = [(a, b, c, d) for a in (0, 1, P - 1) for b in (0, P - 1) for c in (0, 2, P - 1) for d in (0, 1, P - 1)]
+    cases2 += [tuple(rnd.randrange(P) for _ in range(4)) for _ in range(iters // 3)]
+    for a0, a1, b0, b1 in cases2:
+        inp = {}
+        for c, v in (("x", a0), ("y", a1), ("z", b0), ("w", b1)):
+            inp.update({"%s%d" % (c, i): l for i, l in enumerate(limbs(v))})
+        o = f2m.run(inp)
+        assert unl(o[:N]) == (a0 * b0 - a1 * b1) * rinv % P and unl(o[N:]) == (a0 * b1 + a1 * b0) * rinv % P, ("fp2_mul", a0, a1, b0, b1)
+        o = f2s.run(inp)
+        assert unl(o[:N]) == (a0 * a0 - a1 * a1) * rinv % P and unl(o[N:]) == 2 * a0 * a1 * rinv % P, ("fp2_sqr", a0, a1)
+    # the wide multiplier alone on full-range operands (no dropped carry for any 256-bit input)
+    mw = Prog("mul_wide", ["x%d" % i for i in range(N)] + ["y%d" % i for i in range(N)], [])
+    mw.outs = mul_wide(mw, ["x%d" % i for i in range(N)], ["y%d" % i for i in range(N)])
+    for a0, b0 in [(top, top), (top, 1), (1 << 255, top), (P, P)] + [(rnd.getrandbits(256), rnd.getrandbits(256)) for _ in range(iters // 3)]:
+        inp = {"x%d" % i: l for i, l in enumerate(limbs(a0))}
+        inp.update({"y%d" % i: l for i, l in enumerate(limbs(b0))})
+        assert sum(v << (32 * i) for i, v in enumerate(mw.run(inp))) == a0 * b0
     if verbose:
+        print("fp2_mul: %d IMAD.WIDE-equivalent pairs, %d add/sub/logic ops; fp2_sqr: %d pairs; all %d cases ok"
+              % ((f2m.count("mad") + f2m.count("mul") - 16) // 2, f2m.count("add") + f2m.count("sub") + f2m.count("and") + f2m.count("selp"),
+                 (f2s.count("mad") + f2s.count("mul") - 16) // 2, len(cases2)))
         print("fp_mul: %d mad/mul ops (%d IMAD.WIDE-equivalent pairs + %d single), %d add/sub ops; all %d cases ok"
               % (mul.count("mad") + mul.count("mul"), (mul.count("mad") + mul.count("mul") - 8) // 2, 8,
                  mul.count("add") + mul.count("sub"), len(cases)))
@@ -250,6 +380,12 @@ def render():
     for prog, sig in ((gen_mul(), "const uint32_t* a, const uint32_t* b"), (gen_add(), "const uint32_t* a, const uint32_t* b"),
                       (gen_sub(), "const uint32_t* a, const uint32_t* b")):
         out.append("__device__ __forceinline__ void %s_ptx(uint32_t* r, %s) {\n%s\n}\n" % (prog.name, sig, prog.cuda()))
+    out.append("// (r + q u) = (x + y u)(z + w u): lazily reduced, 3 x 64 + 2 x 72 IMAD.WIDE\n"
+               "__device__ __forceinline__ void fp2_mul_ptx(uint32_t* r, uint32_t* q, const uint32_t* x, const uint32_t* y, const uint32_t* z, const uint32_t* w) {\n%s\n}\n"
+               % gen_fp2_mul().cuda())
+    out.append("// (r + q u) = (x + y u)^2\n"
+               "__device__ __forceinline__ void fp2_sqr_ptx(uint32_t* r, uint32_t* q, const uint32_t* x, const uint32_t* y) {\n%s\n}\n"
+               % gen_fp2_sqr().cuda())
     return "\n".join(out)
 
 
