@@ -143,6 +143,10 @@ int zkv_g2_check_batch(const uint8_t* g2s, size_t n, uint8_t* out, int device);
 /* timing of the stage kernels of the last *_device / host call on `device`, milliseconds, for bench.py:
  * [0] decode+hash [1] vk_x [2] g2 check [3] miller [4] final exp ; returns number of entries */
 int zkv_last_stage_ms(const void* handle_vk, int device, float* out, int cap);
+/* A device batch is cut into `chunks` pieces whose kernel chains run on side streams of the device context, so the partial last wave of
+ * one kernel is back-filled by blocks of another (default 2; batches under 8192 proofs are never cut).  chunks = 1 runs one chain on the
+ * main stream and records the per-stage events zkv_last_stage_ms reads.  Process-wide; returns the previous value. */
+int zkv_set_overlap(int chunks);
 /* integer-pipe microbenchmark (roofline denominator): returns measured IMAD.WIDE.U32 results/s and
  * Fp-multiplications/s on `device` */
 int zkv_imad_peak(int device, double* wide_per_s, double* fpmul_per_s);

@@ -50,6 +50,7 @@ _SIGS = {
     "zkv_last_stage_ms": (C.c_int, [_P, C.c_int, _P, C.c_int]),
     "zkv_risc0_vk": (_P, [_P]),
     "zkv_sp1_vk": (_P, [_P]),
+    "zkv_set_overlap": (C.c_int, [C.c_int]),
     "zkv_imad_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 EXPORTS = tuple(_SIGS)

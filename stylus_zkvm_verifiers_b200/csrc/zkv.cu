@@ -67,6 +67,11 @@ struct DevCtx {
     uint8_t* h_pin = nullptr; size_t h_pin_cap = 0; uint8_t* h_out = nullptr; size_t h_out_cap = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float stage_ms[5] = {0, 0, 0, 0, 0};
+    // overlap: a batch is cut into chunks whose kernel chains run on side streams, so the block scheduler back-fills the partial last
+    // wave of one chunk's kernel with blocks of another chunk's (see run_verify)
+    static constexpr int NAUX = 4;
+    cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr, nullptr, nullptr};
     std::mutex mu;
 };
 
@@ -99,6 +104,9 @@ static void ctx_free(DevCtx* c) {
     cudaFree(c->d_in); cudaFree(c->d_out); cudaFreeHost(c->h_pin); cudaFreeHost(c->h_out);
     cudaFree(c->d_vk); cudaFree(c->d_lines); cudaFree(c->d_pre); cudaFree(c->d_tab); cudaFree(c->d_ic0);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_join) if (e) cudaEventDestroy(e);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (auto& a : c->aux) if (a) cudaStreamDestroy(a);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -117,6 +125,9 @@ static int vk_build_on(zkv_vk* vk, DevCtx* c) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
+    for (auto& a : c->aux) CK(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (auto& e : c->ev_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     int nt = vk->n_ic - 1;
     CK(cudaMalloc(&c->d_vk, sizeof(VkDev))); CK(cudaMalloc(&c->d_lines, sizeof(line_t) * 3 * ZKV_LINES_PER_G2)); CK(cudaMalloc(&c->d_pre, sizeof(fp12)));
     CK(cudaMalloc(&c->d_tab, sizeof(g1aff) * (size_t)nt * ZKV_WIN_PER_SCALAR * ZKV_WIN_ENTRIES)); CK(cudaMalloc(&c->d_ic0, sizeof(g1aff)));
@@ -193,47 +204,76 @@ __global__ void k_status_all_fail(int n, const uint8_t* flags, uint8_t* status) 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) status[i] = (flags[i] & F_SELMIS) ? ST_SELECTOR_MISMATCH : ST_VERIFICATION_FAILED;
 }
-// enqueue all stages of one batch on c->stream (asynchronous); caller holds c->mu and has set the device
-static int run_verify(DevCtx* c, const Job& j) {
-    const zkv_vk* vk = j.vk; int n = (int)j.n;
-    if (n == 0) return 0;
+// Number of chunks a device batch is cut into (each chunk's kernel chain runs on its own side stream).  1 = one chain on the main stream
+// with per-stage events (what bench.py uses for the per-kernel roofline figures).
+static int g_overlap_chunks = 2;
+extern "C" int zkv_set_overlap(int chunks) { int old = g_overlap_chunks; if (chunks >= 1 && chunks <= 64) g_overlap_chunks = chunks; return old; }
+
+// the kernel chain for proofs [o, o+m) of job j on stream s; stage events only when `timed`
+static int enqueue_chain(DevCtx* c, const Job& j, size_t o, int m, cudaStream_t s, bool timed) {
+    const zkv_vk* vk = j.vk;
     int ns = (j.mode == SIG_GENERIC) ? j.k : 2;
-    int rc = ctx_reserve(c, j.n, (size_t)ns * 8); if (rc) return rc;
-    cudaStream_t s = c->stream;
-    CK(cudaEventRecord(c->ev[0], s));
-    k_decode<<<nblk(n), TPB, 0, s>>>(n, j.recs, j.stride, j.off, j.selector_le, j.check_selector, vk->vm, c->px[0], c->py[0], c->qx, c->qy, c->px[3], c->py[3], c->flags);
+    uint32_t* scal = c->scal + o * (size_t)ns * 8;
+    uint8_t* flags = c->flags + o;
+    if (timed) CK(cudaEventRecord(c->ev[0], s));
+    k_decode<<<nblk(m), TPB, 0, s>>>(m, j.recs + o * j.stride, j.stride, j.off, j.selector_le, j.check_selector, vk->vm, c->px[0] + o, c->py[0] + o, c->qx + o, c->qy + o, c->px[3] + o, c->py[3] + o, flags);
     const g1aff* tab = c->d_tab; int nwin = ZKV_WIN_PER_SCALAR;
     switch (j.mode) {
-        case SIG_GENERIC: k_generic_signals<<<nblk(n), TPB, 0, s>>>(n, j.k, j.sig_a, c->scal, c->flags); break;
-        case SIG_RISC0_VERIFY: k_risc0_signals<<<nblk(n), TPB, 0, s>>>(n, j.sig_a, j.sig_b, nullptr, 0, j.hc, c->scal); break;
-        case SIG_RISC0_INTEGRITY: k_risc0_signals<<<nblk(n), TPB, 0, s>>>(n, nullptr, nullptr, j.sig_a, 1, j.hc, c->scal); break;
-        case SIG_SP1: k_sp1_signals<<<nblk(n), TPB, 0, s>>>(n, j.sig_a, j.sig_b, j.pv_off, j.pv_stride, c->scal, c->flags); break;
+        case SIG_GENERIC: k_generic_signals<<<nblk(m), TPB, 0, s>>>(m, j.k, j.sig_a + o * (size_t)j.k * 32, scal, flags); break;
+        case SIG_RISC0_VERIFY: k_risc0_signals<<<nblk(m), TPB, 0, s>>>(m, j.sig_a + o * 32, j.sig_b + o * 32, nullptr, 0, j.hc, scal); break;
+        case SIG_RISC0_INTEGRITY: k_risc0_signals<<<nblk(m), TPB, 0, s>>>(m, nullptr, nullptr, j.sig_a + o * 32, 1, j.hc, scal); break;
+        case SIG_SP1: k_sp1_signals<<<nblk(m), TPB, 0, s>>>(m, j.sig_a + o * 32, j.pv_off ? j.sig_b : j.sig_b + o * j.pv_stride, j.pv_off ? j.pv_off + o : nullptr, j.pv_stride, scal, flags); break;
     }
     if (j.mode == SIG_RISC0_VERIFY || j.mode == SIG_RISC0_INTEGRITY) { tab = c->d_tab + (size_t)2 * ZKV_WIN_PER_SCALAR * ZKV_WIN_ENTRIES; nwin = 32; }   // claim_lo / claim_hi are 128-bit
-    CK(cudaEventRecord(c->ev[1], s));
+    if (timed) CK(cudaEventRecord(c->ev[1], s));
     if (j.all_fail || !vk->valid) {
-        k_status_all_fail<<<nblk(n), TPB, 0, s>>>(n, c->flags, j.d_status);
-        for (int e = 2; e < 6; e++) CK(cudaEventRecord(c->ev[e], s));
+        k_status_all_fail<<<nblk(m), TPB, 0, s>>>(m, flags, j.d_status + o);
+        if (timed) for (int e = 2; e < 6; e++) CK(cudaEventRecord(c->ev[e], s));
         CK(cudaGetLastError());
         return 0;
     }
-    k_vkx<<<nblk(n), TPB, 0, s>>>(n, c->scal, ns, nwin, tab, j.base, c->px[2], c->py[2], c->flags);
-    CK(cudaEventRecord(c->ev[2], s));
-    k_g2_check<<<nblk(n), TPB, 0, s>>>(n, c->qx, c->qy, c->flags);
-    CK(cudaEventRecord(c->ev[3], s));
+    k_vkx<<<nblk(m), TPB, 0, s>>>(m, scal, ns, nwin, tab, j.base, c->px[2] + o, c->py[2] + o, flags);
+    if (timed) CK(cudaEventRecord(c->ev[2], s));
+    k_g2_check<<<nblk(m), TPB, 0, s>>>(m, c->qx + o, c->qy + o, flags);
+    if (timed) CK(cudaEventRecord(c->ev[3], s));
     MillerArgs a; memset(&a, 0, sizeof a);
-    a.px[0] = c->px[0]; a.py[0] = c->py[0]; a.px[1] = c->px[2]; a.py[1] = c->py[2]; a.px[2] = c->px[3]; a.py[2] = c->py[3];
-    a.qx = c->qx; a.qy = c->qy;
+    a.px[0] = c->px[0] + o; a.py[0] = c->py[0] + o; a.px[1] = c->px[2] + o; a.py[1] = c->py[2] + o; a.px[2] = c->px[3] + o; a.py[2] = c->py[3] + o;
+    a.qx = c->qx + o; a.qy = c->qy + o;
     a.tabs[0] = c->d_lines + 1 * ZKV_LINES_PER_G2; a.tabs[1] = c->d_lines + 2 * ZKV_LINES_PER_G2;
     a.nfixed = 2; a.pre = c->d_pre;
     a.skip_bit[0] = F_SKIP0; a.skip_bit[1] = F_SKIPX; a.skip_bit[2] = F_SKIPC;
     a.vk_skip = (uint8_t)((c->h_vk.g2_inf[1] ? 2 : 0) | (c->h_vk.g2_inf[2] ? 4 : 0));
-    k_miller<<<nblk(n, ZKV_HTPB), ZKV_HTPB, 0, s>>>(n, a, c->flags, c->f);
-    CK(cudaEventRecord(c->ev[4], s));
-    k_final_exp<<<nblk(n, ZKV_HTPB), ZKV_HTPB, 0, s>>>(n, c->f, c->flags, j.d_status, nullptr, 0);
-    CK(cudaEventRecord(c->ev[5], s));
+    k_miller<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, a, flags, c->f + o);
+    if (timed) CK(cudaEventRecord(c->ev[4], s));
+    k_final_exp<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, c->f + o, flags, j.d_status + o, nullptr, 0);
+    if (timed) CK(cudaEventRecord(c->ev[5], s));
     CK(cudaGetLastError());
     return 0;
+}
+// Fork `chunks` side streams off `main`, run fn(chunk_begin, chunk_len, stream) on them round-robin, join back into `main`.
+// Chunk boundaries are multiples of the heavy kernels' block size so no chunk carries a second partial block.
+template <class F>
+static int fork_join(DevCtx* c, cudaStream_t main, size_t n, int chunks, F fn) {
+    size_t per = (n + chunks - 1) / chunks;
+    per = (per + ZKV_HTPB - 1) / ZKV_HTPB * ZKV_HTPB;
+    CK(cudaEventRecord(c->ev_fork, main));
+    int used = 0, k = 0;
+    for (size_t o = 0; o < n; o += per, k++) {
+        cudaStream_t s = c->aux[k % DevCtx::NAUX];
+        if (k < DevCtx::NAUX) { CK(cudaStreamWaitEvent(s, c->ev_fork, 0)); used = k + 1; }
+        int rc = fn(o, (int)std::min(per, n - o), s); if (rc) return rc;
+    }
+    for (int a = 0; a < used; a++) { CK(cudaEventRecord(c->ev_join[a], c->aux[a])); CK(cudaStreamWaitEvent(main, c->ev_join[a], 0)); }
+    return 0;
+}
+// enqueue all stages of one batch (asynchronous; completion is ordered on c->stream); caller holds c->mu and has set the device
+static int run_verify(DevCtx* c, const Job& j) {
+    if (j.n == 0) return 0;
+    int ns = (j.mode == SIG_GENERIC) ? j.k : 2;
+    int rc = ctx_reserve(c, j.n, (size_t)ns * 8); if (rc) return rc;
+    int chunks = g_overlap_chunks;
+    if (j.n < (size_t)8192 || chunks <= 1) return enqueue_chain(c, j, 0, (int)j.n, c->stream, true);
+    return fork_join(c, c->stream, j.n, chunks, [&](size_t o, int m, cudaStream_t s) { return enqueue_chain(c, j, o, m, s, false); });
 }
 static void collect_stage_ms(DevCtx* c) {
     for (int e = 0; e < 5; e++) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[e], c->ev[e + 1]) != cudaSuccess) { cudaGetLastError(); ms = 0; } c->stage_ms[e] = ms; }
@@ -521,34 +561,40 @@ extern "C" int zkv_sp1_verify_batch_device(const zkv_sp1* h, int device, const v
 }
 
 // ------------------------------------------------------------------------------------------ pairing service (0x08 seam)
-static int run_pairing4(DevCtx* c, const zkv_vk* vk, size_t n_, const uint8_t* d_g1s, const uint8_t* d_g2s, uint8_t* d_ok, uint8_t* d_gt, uint8_t* d_miller) {
-    int n = (int)n_;
-    int rc = ctx_reserve(c, n_, 8); if (rc) return rc;
-    cudaStream_t s = c->stream;
-    CK(cudaEventRecord(c->ev[0], s));
-    k_g1_decode4<<<nblk(n), TPB, 0, s>>>(n, d_g1s, d_g2s, c->px[0], c->py[0], c->px[1], c->py[1], c->px[2], c->py[2], c->px[3], c->py[3], c->qx, c->qy, c->flags);
-    CK(cudaEventRecord(c->ev[1], s)); CK(cudaEventRecord(c->ev[2], s));
-    if (!vk->valid) {   // a fixed G2 point is invalid: every call reverts
-        CK(cudaMemsetAsync(d_ok, 2, n_, s)); if (d_gt) CK(cudaMemsetAsync(d_gt, 0, n_ * 384, s)); if (d_miller) CK(cudaMemsetAsync(d_miller, 0, n_ * 384, s));
-        for (int e = 3; e < 6; e++) CK(cudaEventRecord(c->ev[e], s));
-        return 0;
-    }
-    k_g2_check<<<nblk(n), TPB, 0, s>>>(n, c->qx, c->qy, c->flags);
-    CK(cudaEventRecord(c->ev[3], s));
+static int pairing4_chain(DevCtx* c, const zkv_vk* vk, size_t o, int n, const uint8_t* d_g1s, const uint8_t* d_g2s, uint8_t* d_ok, uint8_t* d_gt, uint8_t* d_miller, cudaStream_t s, bool timed) {
+    uint8_t* flags = c->flags + o;
+    if (timed) CK(cudaEventRecord(c->ev[0], s));
+    k_g1_decode4<<<nblk(n), TPB, 0, s>>>(n, d_g1s + o * 256, d_g2s + o * 128, c->px[0] + o, c->py[0] + o, c->px[1] + o, c->py[1] + o, c->px[2] + o, c->py[2] + o, c->px[3] + o, c->py[3] + o, c->qx + o, c->qy + o, flags);
+    if (timed) { CK(cudaEventRecord(c->ev[1], s)); CK(cudaEventRecord(c->ev[2], s)); }
+    k_g2_check<<<nblk(n), TPB, 0, s>>>(n, c->qx + o, c->qy + o, flags);
+    if (timed) CK(cudaEventRecord(c->ev[3], s));
     MillerArgs a; memset(&a, 0, sizeof a);
-    for (int j = 0; j < 4; j++) { a.px[j] = c->px[j]; a.py[j] = c->py[j]; }
-    a.qx = c->qx; a.qy = c->qy;
+    for (int j = 0; j < 4; j++) { a.px[j] = c->px[j] + o; a.py[j] = c->py[j] + o; }
+    a.qx = c->qx + o; a.qy = c->qy + o;
     for (int j = 0; j < 3; j++) a.tabs[j] = c->d_lines + (size_t)j * ZKV_LINES_PER_G2;
     a.nfixed = 3; a.pre = nullptr;
     a.skip_bit[0] = F_SKIP0; a.skip_bit[1] = 0x20; a.skip_bit[2] = 0x40; a.skip_bit[3] = 0x80;
     a.vk_skip = (uint8_t)((c->h_vk.g2_inf[0] ? 2 : 0) | (c->h_vk.g2_inf[1] ? 4 : 0) | (c->h_vk.g2_inf[2] ? 8 : 0));
-    k_miller<<<nblk(n, ZKV_HTPB), ZKV_HTPB, 0, s>>>(n, a, c->flags, c->f);
-    CK(cudaEventRecord(c->ev[4], s));
-    if (d_miller) k_f12_to_bytes<<<nblk(n), TPB, 0, s>>>(n, c->f, d_miller);
-    k_final_exp<<<nblk(n, ZKV_HTPB), ZKV_HTPB, 0, s>>>(n, c->f, c->flags, d_ok, d_gt, 1);
-    CK(cudaEventRecord(c->ev[5], s));
+    k_miller<<<nblk(n, ZKV_HTPB), ZKV_HTPB, 0, s>>>(n, a, flags, c->f + o);
+    if (timed) CK(cudaEventRecord(c->ev[4], s));
+    if (d_miller) k_f12_to_bytes<<<nblk(n), TPB, 0, s>>>(n, c->f + o, d_miller + o * 384);
+    k_final_exp<<<nblk(n, ZKV_HTPB), ZKV_HTPB, 0, s>>>(n, c->f + o, flags, d_ok + o, d_gt ? d_gt + o * 384 : nullptr, 1);
+    if (timed) CK(cudaEventRecord(c->ev[5], s));
     CK(cudaGetLastError());
     return 0;
+}
+static int run_pairing4(DevCtx* c, const zkv_vk* vk, size_t n_, const uint8_t* d_g1s, const uint8_t* d_g2s, uint8_t* d_ok, uint8_t* d_gt, uint8_t* d_miller) {
+    if (n_ == 0) return 0;
+    int rc = ctx_reserve(c, n_, 8); if (rc) return rc;
+    cudaStream_t s = c->stream;
+    if (!vk->valid) {   // a fixed G2 point is invalid: every call reverts
+        CK(cudaMemsetAsync(d_ok, 2, n_, s)); if (d_gt) CK(cudaMemsetAsync(d_gt, 0, n_ * 384, s)); if (d_miller) CK(cudaMemsetAsync(d_miller, 0, n_ * 384, s));
+        for (int e = 0; e < 6; e++) CK(cudaEventRecord(c->ev[e], s));
+        return 0;
+    }
+    int chunks = g_overlap_chunks;
+    if (n_ < (size_t)8192 || chunks <= 1) return pairing4_chain(c, vk, 0, (int)n_, d_g1s, d_g2s, d_ok, d_gt, d_miller, s, true);
+    return fork_join(c, s, n_, chunks, [&](size_t o, int m, cudaStream_t st) { return pairing4_chain(c, vk, o, m, d_g1s, d_g2s, d_ok, d_gt, d_miller, st, false); });
 }
 extern "C" int zkv_pairing4_batch(const zkv_vk* vk, const uint8_t* g1s, const uint8_t* g2s, size_t n, uint8_t* ok_out, uint8_t* gt_out, uint8_t* miller_out) {
     if (!vk || (n && (!g1s || !g2s || !ok_out))) return fail(ZKV_ERR_ARG, "zkv_pairing4_batch: null argument");

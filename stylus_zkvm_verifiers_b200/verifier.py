@@ -289,6 +289,11 @@ def g2_check_batch(g2s, n, device=0):
     return out
 
 
+def set_overlap(chunks):
+    """Chunks a device batch is cut into for stream overlap (1 = serial chain with per-stage timing); returns the previous value."""
+    return N.lib().zkv_set_overlap(int(chunks))
+
+
 def imad_peak(device=0):
     w, f = C.c_double(0), C.c_double(0)
     N.check(N.lib().zkv_imad_peak(device, C.byref(w), C.byref(f)))
