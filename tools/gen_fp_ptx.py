@@ -25,6 +25,8 @@ M0 = (-pow(P, -1, 1 << 32)) & MASK
 assert M0 == 0xE4866389
 PL = [(P >> (32 * i)) & MASK for i in range(N)]
 RMONT = 1 << 256
+GRAIN_MUL = int(os.environ.get("ZKV_GRAIN_MUL", "1"))      # carry chains emitted per stream per round of interleave()
+GRAIN_REDC = int(os.environ.get("ZKV_GRAIN_REDC", "1"))
 
 
 class Prog:
@@ -280,6 +282,55 @@ def sub_mod(p, a, b):
     return [p.op("add.cc" if k == 0 else ("addc.cc" if k < 7 else "addc"), d[k], pm[k]) for k in range(N)]
 
 
+def _reads_cf(op):
+    return op.startswith(("madc", "addc", "subc"))
+
+
+def _writes_cf(op):
+    return op.endswith(".cc")
+
+
+def interleave(p, builders, grain=1):
+    """Run each builder (it emits into p), then merge the instruction streams round-robin at carry-chain granularity (a cut is only
+    made where CC.CF is dead), `grain` chains at a time.  The streams must be independent of each other.  ptxas keeps the source order
+    as its tie-break, so this is what puts several independent IMAD.WIDE.X carry chains in flight per warp: one chain alone issues
+    an instruction per carry-predicate latency, not per pipe slot."""
+    results, streams = [], []
+    for b in builders:
+        start = len(p.code)
+        results.append(b())
+        streams.append(p.code[start:])
+        del p.code[start:]
+    segs = []
+    for code in streams:
+        live = [False] * (len(code) + 1)
+        for k in range(len(code) - 1, -1, -1):
+            op = code[k][0]
+            if op == "assert_nc":
+                live[k] = live[k + 1]
+            elif _reads_cf(op):
+                live[k] = True
+            elif _writes_cf(op):
+                live[k] = False
+            else:
+                live[k] = live[k + 1]
+        out, cur = [], []
+        for k, ins in enumerate(code):
+            if cur and not live[k] and ins[0] != "assert_nc":
+                out.append(cur); cur = []
+            cur.append(ins)
+        if cur:
+            out.append(cur)
+        segs.append(out)
+    pos = [0] * len(segs)
+    while any(pos[i] < len(segs[i]) for i in range(len(segs))):
+        for i in range(len(segs)):
+            for _ in range(grain):
+                if pos[i] < len(segs[i]):
+                    p.code.extend(segs[i][pos[i]]); pos[i] += 1
+    return results
+
+
 def gen_fp2_mul():
     """(r, q) = (x + y u)(z + w u) in Fp[u]/(u^2+1):  r = xz - yw,  q = (x+y)(z+w) - xz - yw."""
     nm = lambda c: ["%s%d" % (c, i) for i in range(N)]
@@ -287,10 +338,7 @@ def gen_fp2_mul():
     p = Prog("fp2_mul", x + y + z + w, nm("r") + nm("q"))
     s = add_raw(p, x, y)                    # < 2P < 2^255
     t = add_raw(p, z, w)
-    T0 = mul_wide(p, x, z)
-    T1 = mul_wide(p, y, w)
-    T2 = mul_wide(p, s, t)                  # < 4 P^2 < 2^510; issued before the carry work on T0/T1 so that ptxas can run that work in the
-                                            # shadow of these multiplies (IMAD.WIDE issues every 4th cycle, the ALU chains fill the gaps)
+    T0, T1, T2 = interleave(p, [lambda: mul_wide(p, x, z), lambda: mul_wide(p, y, w), lambda: mul_wide(p, s, t)], GRAIN_MUL)   # T2 < 4 P^2 < 2^510
     # C0 = T0 - T1 (+ P * 2^256 if negative)  in [0, P * 2^256)
     d = [p.op("sub.cc" if k == 0 else "subc.cc", T0[k], T1[k]) for k in range(2 * N)]
     bor = p.op("subc", 0, 0)
@@ -299,8 +347,7 @@ def gen_fp2_mul():
     S = add_raw(p, T0, T1, 2 * N)           # < 2 P^2
     C1 = [p.op("sub.cc" if k == 0 else "subc.cc", T2[k], S[k]) for k in range(2 * N)]
     p.emit("assert_nc", None)               # xw + yz >= 0
-    redc_wide(p, C0, nm("r"))
-    redc_wide(p, C1, nm("q"))
+    interleave(p, [lambda: redc_wide(p, C0, nm("r")), lambda: redc_wide(p, C1, nm("q"))], GRAIN_REDC)
     return p
 
 
@@ -312,8 +359,8 @@ def gen_fp2_sqr():
     s = add_raw(p, x, y)
     d = sub_mod(p, x, y)
     m = add_raw(p, x, x)
-    redc_wide(p, mul_wide(p, s, d), nm("r"))
-    redc_wide(p, mul_wide(p, m, y), nm("q"))
+    A, B = interleave(p, [lambda: mul_wide(p, s, d), lambda: mul_wide(p, m, y)], GRAIN_MUL)
+    interleave(p, [lambda: redc_wide(p, A, nm("r")), lambda: redc_wide(p, B, nm("q"))], GRAIN_REDC)
     return p
 
 
