@@ -46,6 +46,7 @@ _SIGS = {
     "zkv_g2_mul_batch": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, C.c_int]),
     "zkv_vk_x_batch": (C.c_int, [_P, _P, C.c_int, C.c_size_t, _P]),
     "zkv_fp_mul_batch": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_int]),
+    "zkv_fp12_op_batch": (C.c_int, [C.c_int, _P, _P, C.c_size_t, _P, C.c_int]),
     "zkv_g2_check_batch": (C.c_int, [_P, C.c_size_t, _P, C.c_int]),
     "zkv_last_stage_ms": (C.c_int, [_P, C.c_int, _P, C.c_int]),
     "zkv_risc0_vk": (_P, [_P]),

@@ -227,6 +227,27 @@ __global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_final_exp(int n, co
     status[i] = pairing_mode ? (one ? 1 : 0) : (one ? ST_OK : ST_VERIFICATION_FAILED);
     if (gt_out) f12_to_bytes(gt_out + (size_t)i * 384, gt);
 }
+// parity hook: one Fp12 tower operation per thread on byte operands (12 x BE-32 each, tower order).
+// op 0: a*b  1: a^2  2: a * line(b.c0.c0, b.c0.c1, b.c0.c2)  3: cyclotomic square  4: 1/a  5..7: Frobenius^(op-4)  8: final exponentiation
+__global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_fp12_op(int n, int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = i0 < n ? i0 : n - 1;                      // every thread runs the operation: the tower routines contain block-wide rendezvous
+    fp12 x, y, z; fp* xw = &x.c0.c0.c0; fp* yw = &y.c0.c0.c0;
+    for (int k = 0; k < 12; k++) {
+        fp t; be32_to_raw(t.v, a + (size_t)i * 384 + 32 * k); fp_to_mont(xw[k], t);
+        if (b) { be32_to_raw(t.v, b + (size_t)i * 384 + 32 * k); fp_to_mont(yw[k], t); } else yw[k] = fp_zero();
+    }
+    switch (op) {
+        case 0: f12_mul(z, x, y); break;
+        case 1: f12_sqr(z, x); break;
+        case 2: z = x; f12_mul_line(z, y.c0.c0, y.c0.c1, y.c0.c2); break;
+        case 3: f12_cyc_sqr(z, x); break;
+        case 4: f12_inv(z, x); break;
+        case 5: case 6: case 7: f12_frob(z, x, op - 4); break;
+        default: final_exp(z, x); break;
+    }
+    if (i0 < n) f12_to_bytes(out + (size_t)i * 384, z);
+}
 __global__ void k_f12_to_bytes(int n, const fp12* in, uint8_t* out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { fp12 t = in[i]; f12_to_bytes(out + (size_t)i * 384, t); }

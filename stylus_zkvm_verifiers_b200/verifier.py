@@ -283,6 +283,13 @@ def fp_mul_batch(a, b, n, device=0):
     return out
 
 
+def fp12_op_batch(op, a, b, n, device=0):
+    """Fp12 tower operation `op` (see zkv.h) on n operands of 384 bytes; b may be None for unary operations."""
+    out = C.create_string_buffer(384 * n)
+    N.check(N.lib().zkv_fp12_op_batch(op, N.buf(a), N.buf(b) if b is not None else None, n, out, device))
+    return out.raw
+
+
 def g2_check_batch(g2s, n, device=0):
     out = np.zeros(n, dtype=np.uint8)
     N.check(N.lib().zkv_g2_check_batch(N.buf(g2s), n, out.ctypes.data, device))

@@ -38,6 +38,45 @@ def test_fp_mul(Z):
         assert out[32 * i:32 * i + 32] == w32(x * y % P), (hex(x), hex(y))
 
 
+def test_fp12_tower_ops(Z):
+    """Every Fp12 routine the pairing kernels are built from, against the oracle's tower (bit-exact, 12 x BE-32)."""
+    from stylus_zkvm_verifiers_b200.synth import SplitMix64
+    rng = SplitMix64(12)
+    n = 200                                           # more than one block: the routines rendezvous block-wide
+    rnd12 = lambda: b"".join(w32(rng.u256() % P) for _ in range(12))
+    one = w32(1) + bytes(352)
+    A = [rnd12() for _ in range(n)]; B = [rnd12() for _ in range(n)]
+    A[0] = one; B[1] = one; A[2] = b"".join(w32(P - 1) for _ in range(12)); B[2] = A[2]; A[3] = bytes(384)
+    a, b = b"".join(A), b"".join(B)
+    mul = Z.fp12_op_batch(0, a, b, n)
+    sqr = Z.fp12_op_batch(1, a, None, n)
+    inv = Z.fp12_op_batch(4, a, None, n)
+    for i in range(n):
+        assert mul[384 * i:384 * i + 384] == O.fp12_mul(A[i], B[i]), ("mul", i)
+        assert sqr[384 * i:384 * i + 384] == O.fp12_mul(A[i], A[i]), ("sqr", i)
+        if i != 3:
+            assert O.fp12_mul(A[i], inv[384 * i:384 * i + 384]) == one, ("inv", i)
+    # sparse line product: a * (l0 + l3 w + l4 v w) == a * dense(l0,0,0 | l3,l4,0)
+    L = [B[i][:192] for i in range(n)]
+    dense = [L[i][0:64] + bytes(128) + L[i][64:192] + bytes(64) for i in range(n)]
+    line = Z.fp12_op_batch(2, a, b"".join(L[i] + bytes(192) for i in range(n)), n)
+    for i in range(n):
+        assert line[384 * i:384 * i + 384] == O.fp12_mul(A[i], dense[i]), ("line", i)
+    # Frobenius: x^(p^k) for k = 1, 2, 3 must be multiplicative and frob1 o frob1 = frob2, frob1 o frob2 = frob3
+    f1 = Z.fp12_op_batch(5, a, None, n); f2 = Z.fp12_op_batch(6, a, None, n); f3 = Z.fp12_op_batch(7, a, None, n)
+    assert Z.fp12_op_batch(5, f1, None, n) == f2 and Z.fp12_op_batch(5, f2, None, n) == f3
+    fm = Z.fp12_op_batch(5, mul, None, n); fb = Z.fp12_op_batch(5, b, None, n)
+    assert Z.fp12_op_batch(0, f1, fb, n) == fm
+    # final exponentiation and cyclotomic squaring (on elements of the cyclotomic subgroup = final-exponentiation outputs)
+    m = 64
+    fe = Z.fp12_op_batch(8, a[:384 * m], None, m)
+    cs = Z.fp12_op_batch(3, fe, None, m)
+    for i in range(4, m):
+        g = O.final_exp(A[i])
+        assert fe[384 * i:384 * i + 384] == g, ("final_exp", i)
+        assert cs[384 * i:384 * i + 384] == O.fp12_cyc_sqr(g) == O.fp12_mul(g, g), ("cyc_sqr", i)
+
+
 def test_ec_add_mul_services(Z):
     from stylus_zkvm_verifiers_b200.synth import SplitMix64
     rng = SplitMix64(2)
