@@ -31,6 +31,19 @@ W_RISC0_M = W_MILLER3_M + W_FINALEXP_M + 1800 + 40 + 1000
 W_SP1_M = W_MILLER3_M + W_FINALEXP_M + 1800 + 40 + 1700
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` at this workload, from the committed ncu --set full summary
+    (profiles/r1_ncu_summary.json); None if the summary is absent."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))
+        for k in d["kernels"]:
+            if k["kernel"] == kernel:
+                return {"bytes_per_launch": k["dram_bytes_read"] + k["dram_bytes_write"], "proofs_per_launch": k["proofs"], "source": "profiles/r1_ncu_summary.json"}
+    except Exception:
+        pass
+    return None
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -152,7 +165,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="risc0", choices=["risc0", "sp1"])
@@ -277,8 +290,8 @@ def main():
         "e2e": {"value": total / e2e_s, "unit": "verifies/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": n},
         "gpu_launches": 6 * (chunks if n >= 8192 else 1) * args.steps,
         "stage_ms": stage_sum,
-        "roofline": {"bound": "imad", "kernel": "k_miller", "achieved": mac_miller / (miller_ms * 1e-3) / 1e12 if miller_ms else None, "peak": imad_peak / 1e12,
-                     "unit": "TMAC32/s", "frac": (mac_miller / (miller_ms * 1e-3)) / imad_peak if miller_ms else None, "traffic": None,
+        "roofline": {"bound": "imad (integer-multiply issue rate; HBM and tensor cores are not the bound of this path)", "kernel": "k_miller", "achieved": mac_miller / (miller_ms * 1e-3) / 1e12 if miller_ms else None, "peak": imad_peak / 1e12,
+                     "unit": "TMAC32/s", "frac": (mac_miller / (miller_ms * 1e-3)) / imad_peak if miller_ms else None, "traffic": ncu_traffic("k_miller"),
                      "peak_source": "IMAD.WIDE.U32 issue rate measured live on this GPU (zkv_imad_peak); MEASURED_PEAKS.json holds no integer figure",
                      "fpmul_chain_per_s": fpmul_peak,
                      "whole_path_frac": value / world * W_M * M_MAC32 / imad_peak,

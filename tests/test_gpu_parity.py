@@ -346,3 +346,49 @@ def test_full_size_properties(Z, gpu, fx):
     m = 4096
     st = real.verify_batch([fx["seal"]] * m, [fx["image_id"]] * m, [fx["journal_digest"]] * m)
     assert int((st == 0).sum()) == m
+
+
+@pytest.mark.gpu
+def test_scale_sp1_mixed_and_pairing(Z, gpu, fx):
+    """BASELINE configs 3-5 at a size that exercises several waves and the stream-overlap chunks (2^16 SP1-shape proofs, a 2^16 mixed
+    RISC Zero-shape batch, 2^15 pairing instances).  Full batches are checked through what the generator knows by construction (valid
+    proofs accept, every mutated class rejects); a 2048-element prefix is compared 1:1 with the oracle, Fp12 values included."""
+    from stylus_zkvm_verifiers_b200 import synth as S
+    sub = 2048
+    # config 3: SP1 shape, all valid
+    vk = S.make_vk(gpu, 1, 3, 0xB2000003)
+    kv = Z.VerificationKey(1, vk.alpha, vk.beta, vk.gamma, vk.delta, vk.ic)
+    v = Z.Sp1Verifier(kv)
+    n = 1 << 16
+    b = S.make_sp1_batch(gpu, vk, n, 0xB2000003, pool=2048)
+    st = v.verify_batch(b.vkeys, b.public_values, b.proofs)
+    assert int((st == 0).sum()) == n
+    # config 4 (SP1 flavour): mixed classes; expect[] is what the mutation guarantees, the oracle decides the prefix
+    S.mutate_sp1(b, gpu, S.SplitMix64(0xB2000004))
+    st = v.verify_batch(b.vkeys, b.public_values, b.proofs)
+    for i in range(n):
+        if b.expect[i] is not None:
+            assert st[i] == b.expect[i], (i, b.classes[i], int(st[i]))
+    want = O.sp1_verify_batch(oracle_vk(vk), S.SP1_SELECTOR, b.vkeys[:sub], b.public_values[:sub], b.proofs[:sub])
+    assert st[:sub].tolist() == want.tolist()
+    assert {"valid", "tampered", "off_curve", "wrong_subgroup", "infinity", "malformed"} <= set(b.classes)
+    # config 4 (RISC Zero flavour)
+    vk0 = S.make_vk(gpu, 0, 6, 0xB2000001)
+    kv0 = Z.VerificationKey(0, vk0.alpha, vk0.beta, vk0.gamma, vk0.delta, vk0.ic)
+    r = Z.RiscZeroVerifier(kv0); r.initialize(fx["control_root"], fx["bn254_control_id"])
+    b0 = S.make_risc0_batch(gpu, vk0, r.get_selector(), fx["control_root"], fx["bn254_control_id"], fx["sys0"], n, 0xB2000004, pool=2048)
+    S.mutate_risc0(b0, gpu, S.SplitMix64(0xB2000004))
+    st0 = r.verify_batch(b0.seals, b0.image_ids, b0.journals)
+    for i in range(n):
+        if b0.expect[i] is not None:
+            assert st0[i] == b0.expect[i], (i, b0.classes[i], int(st0[i]))
+    ro = O.Risc0Oracle(oracle_vk(vk0)); ro.initialize(fx["control_root"], fx["bn254_control_id"])
+    assert st0[:sub].tolist() == ro.verify_batch(b0.seals[:sub], b0.image_ids[:sub], b0.journals[:sub]).tolist()
+    # config 5: pairing service, ok bits for all, Fp12 values on the prefix
+    m = 1 << 15
+    g1s, g2s, expect = S.make_pairing4_batch(gpu, vk0, m, 0xB2000005, pool=1024)
+    ok, gt, ml = Z.pairing4_batch(kv0, b"".join(g1s), b"".join(g2s), m, want_gt=True, want_miller=True)
+    assert ok.tolist() == expect
+    blob = b"".join(g1s[i][0:64] + g2s[i] + g1s[i][64:128] + vk0.beta + g1s[i][128:192] + vk0.gamma + g1s[i][192:256] + vk0.delta for i in range(sub))
+    ook, ogt, oml = O.pairing4_batch(blob, sub, want_gt=True, want_miller=True)
+    assert ok[:sub].tolist() == list(ook) and bytes(gt[:384 * sub]) == bytes(ogt) and bytes(ml[:384 * sub]) == bytes(oml)
