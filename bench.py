@@ -103,7 +103,7 @@ def make_workload(Z, S, consts, device, n, shape, seed):
     return v, kv, vk, b
 
 
-def cpu_baseline(O, shape, vk, batch, consts, target_s=8.0):
+def cpu_baseline(O, shape, vk, batch, consts, target_s=12.0):
     """The oracle port of the reference path under OpenMP on all host cores, on a bounded prefix of the same batch."""
     import numpy as np
     h = bytes.fromhex
@@ -128,6 +128,9 @@ def run_reference(args, rank, world):
     """--impl reference: the reference path's CPU restatement (oracle port; the Rust reference cannot be built here), all host threads."""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; this arm is the CPU implementation on ALL host threads, and libgomp reads the
+    # variable when the oracle library is loaded
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
     import oracle_lib as O
@@ -290,7 +293,7 @@ def main():
         "e2e": {"value": total / e2e_s, "unit": "verifies/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": n},
         "gpu_launches": 6 * (chunks if n >= 8192 else 1) * args.steps,
         "stage_ms": stage_sum,
-        "roofline": {"bound": "imad (integer-multiply issue rate; HBM and tensor cores are not the bound of this path)", "kernel": "k_miller", "achieved": mac_miller / (miller_ms * 1e-3) / 1e12 if miller_ms else None, "peak": imad_peak / 1e12,
+        "roofline": {"bound": "imad", "bound_note": "integer-multiply (IMAD.WIDE) issue rate; neither HBM nor the tensor cores bound this path (SURVEY 8d)", "kernel": "k_miller", "achieved": mac_miller / (miller_ms * 1e-3) / 1e12 if miller_ms else None, "peak": imad_peak / 1e12,
                      "unit": "TMAC32/s", "frac": (mac_miller / (miller_ms * 1e-3)) / imad_peak if miller_ms else None, "traffic": ncu_traffic("k_miller"),
                      "peak_source": "IMAD.WIDE.U32 issue rate measured live on this GPU (zkv_imad_peak); MEASURED_PEAKS.json holds no integer figure",
                      "fpmul_chain_per_s": fpmul_peak,
