@@ -210,24 +210,25 @@ static int g_overlap_chunks = 2;
 extern "C" int zkv_set_overlap(int chunks) { int old = g_overlap_chunks; if (chunks >= 1 && chunks <= 64) g_overlap_chunks = chunks; return old; }
 
 // the kernel chain for proofs [o, o+m) of job j on stream s; stage events only when `timed`
-static int enqueue_chain(DevCtx* c, const Job& j, size_t o, int m, cudaStream_t s, bool timed) {
+// jo: offset of the first proof inside the job's buffers, o: offset inside the device workspace
+static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cudaStream_t s, bool timed) {
     const zkv_vk* vk = j.vk;
     int ns = (j.mode == SIG_GENERIC) ? j.k : 2;
     uint32_t* scal = c->scal + o * (size_t)ns * 8;
     uint8_t* flags = c->flags + o;
     if (timed) CK(cudaEventRecord(c->ev[0], s));
-    k_decode<<<nblk(m), TPB, 0, s>>>(m, j.recs + o * j.stride, j.stride, j.off, j.selector_le, j.check_selector, vk->vm, c->px[0] + o, c->py[0] + o, c->qx + o, c->qy + o, c->px[3] + o, c->py[3] + o, flags);
+    k_decode<<<nblk(m), TPB, 0, s>>>(m, j.recs + jo * j.stride, j.stride, j.off, j.selector_le, j.check_selector, vk->vm, c->px[0] + o, c->py[0] + o, c->qx + o, c->qy + o, c->px[3] + o, c->py[3] + o, flags);
     const g1aff* tab = c->d_tab; int nwin = ZKV_WIN_PER_SCALAR;
     switch (j.mode) {
-        case SIG_GENERIC: k_generic_signals<<<nblk(m), TPB, 0, s>>>(m, j.k, j.sig_a + o * (size_t)j.k * 32, scal, flags); break;
-        case SIG_RISC0_VERIFY: k_risc0_signals<<<nblk(m), TPB, 0, s>>>(m, j.sig_a + o * 32, j.sig_b + o * 32, nullptr, 0, j.hc, scal); break;
-        case SIG_RISC0_INTEGRITY: k_risc0_signals<<<nblk(m), TPB, 0, s>>>(m, nullptr, nullptr, j.sig_a + o * 32, 1, j.hc, scal); break;
-        case SIG_SP1: k_sp1_signals<<<nblk(m), TPB, 0, s>>>(m, j.sig_a + o * 32, j.pv_off ? j.sig_b : j.sig_b + o * j.pv_stride, j.pv_off ? j.pv_off + o : nullptr, j.pv_stride, scal, flags); break;
+        case SIG_GENERIC: k_generic_signals<<<nblk(m), TPB, 0, s>>>(m, j.k, j.sig_a + jo * (size_t)j.k * 32, scal, flags); break;
+        case SIG_RISC0_VERIFY: k_risc0_signals<<<nblk(m), TPB, 0, s>>>(m, j.sig_a + jo * 32, j.sig_b + jo * 32, nullptr, 0, j.hc, scal); break;
+        case SIG_RISC0_INTEGRITY: k_risc0_signals<<<nblk(m), TPB, 0, s>>>(m, nullptr, nullptr, j.sig_a + jo * 32, 1, j.hc, scal); break;
+        case SIG_SP1: k_sp1_signals<<<nblk(m), TPB, 0, s>>>(m, j.sig_a + jo * 32, j.pv_off ? j.sig_b : j.sig_b + jo * j.pv_stride, j.pv_off ? j.pv_off + jo : nullptr, j.pv_stride, scal, flags); break;
     }
     if (j.mode == SIG_RISC0_VERIFY || j.mode == SIG_RISC0_INTEGRITY) { tab = c->d_tab + (size_t)2 * ZKV_WIN_PER_SCALAR * ZKV_WIN_ENTRIES; nwin = 32; }   // claim_lo / claim_hi are 128-bit
     if (timed) CK(cudaEventRecord(c->ev[1], s));
     if (j.all_fail || !vk->valid) {
-        k_status_all_fail<<<nblk(m), TPB, 0, s>>>(m, flags, j.d_status + o);
+        k_status_all_fail<<<nblk(m), TPB, 0, s>>>(m, flags, j.d_status + jo);
         if (timed) for (int e = 2; e < 6; e++) CK(cudaEventRecord(c->ev[e], s));
         CK(cudaGetLastError());
         return 0;
@@ -245,7 +246,7 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t o, int m, cudaStream_t 
     a.vk_skip = (uint8_t)((c->h_vk.g2_inf[1] ? 2 : 0) | (c->h_vk.g2_inf[2] ? 4 : 0));
     k_miller<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, a, flags, c->f + o);
     if (timed) CK(cudaEventRecord(c->ev[4], s));
-    k_final_exp<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, c->f + o, flags, j.d_status + o, nullptr, 0);
+    k_final_exp<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, c->f + o, flags, j.d_status + jo, nullptr, 0);
     if (timed) CK(cudaEventRecord(c->ev[5], s));
     CK(cudaGetLastError());
     return 0;
@@ -272,8 +273,38 @@ static int run_verify(DevCtx* c, const Job& j) {
     int ns = (j.mode == SIG_GENERIC) ? j.k : 2;
     int rc = ctx_reserve(c, j.n, (size_t)ns * 8); if (rc) return rc;
     int chunks = g_overlap_chunks;
-    if (j.n < (size_t)8192 || chunks <= 1) return enqueue_chain(c, j, 0, (int)j.n, c->stream, true);
-    return fork_join(c, c->stream, j.n, chunks, [&](size_t o, int m, cudaStream_t s) { return enqueue_chain(c, j, o, m, s, false); });
+    if (j.n < (size_t)8192 || chunks <= 1) return enqueue_chain(c, j, 0, 0, (int)j.n, c->stream, true);
+    return fork_join(c, c->stream, j.n, chunks, [&](size_t o, int m, cudaStream_t s) { return enqueue_chain(c, j, o, o, m, s, false); });
+}
+static void collect_stage_ms(DevCtx* c);
+
+// Host-buffer form of a batch on one device, pipelined: the batch is cut like run_verify cuts it, and every chunk gets its own
+// pack (into its slice of the pinned staging buffer) -> H2D -> kernel chain -> D2H on a side stream, so packing and copying chunk k+1
+// overlap the kernels of chunk k.  pack(first, count, dst) writes the chunk's input block and returns its size in bytes;
+// job(first, count, d_block) describes the chunk, with pointers into its device input block and d_status = c->d_out + first.
+// in_bytes: upper bound of the whole batch's input.  On return c->h_out[0..m) holds the status bytes.
+template <class Pack, class MakeJob>
+static int host_pipeline(DevCtx* c, size_t m, size_t in_bytes, int ns, Pack pack, MakeJob job) {
+    int rc = ctx_reserve(c, m, (size_t)ns * 8); if (rc) return rc;
+    int chunks = (m < (size_t)8192 || g_overlap_chunks <= 1) ? 1 : g_overlap_chunks;
+    rc = ctx_stage(c, in_bytes + 256 * (size_t)chunks, m); if (rc) return rc;
+    size_t per = (m + chunks - 1) / chunks;
+    per = (per + ZKV_HTPB - 1) / ZKV_HTPB * ZKV_HTPB;
+    size_t in_off = 0; int k = 0, used = 0;
+    for (size_t first = 0; first < m; first += per, k++) {
+        size_t cnt = std::min(per, m - first);
+        cudaStream_t s = chunks == 1 ? c->stream : c->aux[k % DevCtx::NAUX];
+        if (chunks > 1) used = std::max(used, k % DevCtx::NAUX + 1);
+        size_t bytes = pack(first, cnt, c->h_pin + in_off);
+        CK(cudaMemcpyAsync(c->d_in + in_off, c->h_pin + in_off, bytes, cudaMemcpyHostToDevice, s));
+        Job j = job(first, cnt, c->d_in + in_off);
+        rc = enqueue_chain(c, j, 0, first, (int)cnt, s, chunks == 1); if (rc) return rc;
+        CK(cudaMemcpyAsync(c->h_out + first, c->d_out + first, cnt, cudaMemcpyDeviceToHost, s));
+        in_off += (bytes + 255) / 256 * 256;
+    }
+    if (chunks == 1) { CK(cudaStreamSynchronize(c->stream)); collect_stage_ms(c); }
+    else for (int a = 0; a < used; a++) CK(cudaStreamSynchronize(c->aux[a]));
+    return 0;
 }
 static void collect_stage_ms(DevCtx* c) {
     for (int e = 0; e < 5; e++) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[e], c->ev[e + 1]) != cudaSuccess) { cudaGetLastError(); ms = 0; } c->stage_ms[e] = ms; }
@@ -314,16 +345,17 @@ extern "C" int zkv_groth16_verify_batch(const zkv_vk* vk, const uint8_t* proofs,
     return for_each_device(vk, n, [&](DevCtx* c, size_t b, size_t e) -> int {
         for (size_t s0 = b; s0 < e; s0 += MAX_CHUNK) {
             size_t m = std::min(MAX_CHUNK, e - s0);
-            size_t pb = m * 256, sb = m * (size_t)k * 32;
-            int rc = ctx_stage(c, pb + sb, m); if (rc) return rc;
-            memcpy(c->h_pin, proofs + s0 * 256, pb); memcpy(c->h_pin + pb, signals + s0 * (size_t)k * 32, sb);
-            CK(cudaMemcpyAsync(c->d_in, c->h_pin, pb + sb, cudaMemcpyHostToDevice, c->stream));
-            Job j; memset(&j, 0, sizeof j);
-            j.vk = vk; j.n = m; j.recs = c->d_in; j.stride = 256; j.off = 0; j.mode = SIG_GENERIC; j.sig_a = c->d_in + pb; j.k = k; j.base = c->h_ic0; j.d_status = c->d_out;
-            rc = run_verify(c, j); if (rc) return rc;
-            CK(cudaMemcpyAsync(c->h_out, c->d_out, m, cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaStreamSynchronize(c->stream));
-            collect_stage_ms(c);
+            int rc = host_pipeline(c, m, m * (256 + (size_t)k * 32), k,
+                [&](size_t first, size_t cnt, uint8_t* dst) -> size_t {
+                    memcpy(dst, proofs + (s0 + first) * 256, cnt * 256); memcpy(dst + cnt * 256, signals + (s0 + first) * (size_t)k * 32, cnt * (size_t)k * 32);
+                    return cnt * (256 + (size_t)k * 32);
+                },
+                [&](size_t first, size_t cnt, uint8_t* d) -> Job {
+                    Job j; memset(&j, 0, sizeof j);
+                    j.vk = vk; j.n = cnt; j.recs = d; j.stride = 256; j.off = 0; j.mode = SIG_GENERIC; j.sig_a = d + cnt * 256; j.k = k; j.base = c->h_ic0; j.d_status = c->d_out + first;
+                    return j;
+                });
+            if (rc) return rc;
             memcpy(status_out + s0, c->h_out, m);
         }
         return 0;
@@ -438,22 +470,24 @@ static int risc0_batch(const zkv_risc0* h, const uint8_t* seals, const uint64_t*
     return for_each_device(vk, cand.size(), [&](DevCtx* c, size_t b, size_t e) -> int {
         for (size_t s0 = b; s0 < e; s0 += MAX_CHUNK) {
             size_t m = std::min(MAX_CHUNK, e - s0);
-            size_t rb = m * 256, per = integrity ? 32 : 64;
-            int rc = ctx_stage(c, rb + m * per, m); if (rc) return rc;
-            uint8_t* pr = c->h_pin; uint8_t* pa = c->h_pin + rb; uint8_t* pb = pa + m * 32;
-            for (size_t t = 0; t < m; t++) {
-                size_t i = cand[s0 + t];
-                memcpy(pr + t * 256, seals + seal_off[i] + 4, 256); memcpy(pa + t * 32, a32 + i * 32, 32);
-                if (!integrity) memcpy(pb + t * 32, b32 + i * 32, 32);
-            }
-            CK(cudaMemcpyAsync(c->d_in, c->h_pin, rb + m * per, cudaMemcpyHostToDevice, c->stream));
-            Job j; memset(&j, 0, sizeof j);
-            j.vk = vk; j.n = m; j.recs = c->d_in; j.stride = 256; j.off = 0; j.mode = integrity ? SIG_RISC0_INTEGRITY : SIG_RISC0_VERIFY;
-            j.sig_a = c->d_in + rb; j.sig_b = c->d_in + rb + m * 32; j.hc = h->hc; j.base = h->base; j.all_fail = h->all_fail; j.d_status = c->d_out;
-            rc = run_verify(c, j); if (rc) return rc;
-            CK(cudaMemcpyAsync(c->h_out, c->d_out, m, cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaStreamSynchronize(c->stream));
-            collect_stage_ms(c);
+            const size_t per = integrity ? 32 : 64;
+            int rc = host_pipeline(c, m, m * (256 + per), 2,
+                [&](size_t first, size_t cnt, uint8_t* dst) -> size_t {
+                    uint8_t* pa = dst + cnt * 256; uint8_t* pb = pa + cnt * 32;
+                    for (size_t t = 0; t < cnt; t++) {
+                        size_t i = cand[s0 + first + t];
+                        memcpy(dst + t * 256, seals + seal_off[i] + 4, 256); memcpy(pa + t * 32, a32 + i * 32, 32);
+                        if (!integrity) memcpy(pb + t * 32, b32 + i * 32, 32);
+                    }
+                    return cnt * (256 + per);
+                },
+                [&](size_t first, size_t cnt, uint8_t* d) -> Job {
+                    Job j; memset(&j, 0, sizeof j);
+                    j.vk = vk; j.n = cnt; j.recs = d; j.stride = 256; j.off = 0; j.mode = integrity ? SIG_RISC0_INTEGRITY : SIG_RISC0_VERIFY;
+                    j.sig_a = d + cnt * 256; j.sig_b = d + cnt * 288; j.hc = h->hc; j.base = h->base; j.all_fail = h->all_fail; j.d_status = c->d_out + first;
+                    return j;
+                });
+            if (rc) return rc;
             for (size_t t = 0; t < m; t++) status_out[cand[s0 + t]] = c->h_out[t];
         }
         return 0;
@@ -516,24 +550,26 @@ extern "C" int zkv_sp1_verify_batch(const zkv_sp1* h, const uint8_t* vkeys, cons
         for (size_t s0 = b; s0 < e; s0 += MAX_CHUNK) {
             size_t m = std::min(MAX_CHUNK, e - s0);
             size_t pvb = 0; for (size_t t = 0; t < m; t++) { size_t i = cand[s0 + t]; pvb += pv_off[i + 1] - pv_off[i]; }
-            size_t rb = m * 256, kb = m * 32, ob = (m + 1) * 8, pv_at = rb + kb + ob;
-            int rc = ctx_stage(c, pv_at + pvb + 8, m); if (rc) return rc;
-            uint8_t* pr = c->h_pin; uint8_t* pk = pr + rb; uint64_t* po = (uint64_t*)(pk + kb); uint8_t* pp = c->h_pin + pv_at;
-            uint64_t acc = 0;
-            for (size_t t = 0; t < m; t++) {
-                size_t i = cand[s0 + t]; uint64_t len = pv_off[i + 1] - pv_off[i];
-                memcpy(pr + t * 256, proofs + proof_off[i] + 4, 256); memcpy(pk + t * 32, vkeys + i * 32, 32);
-                po[t] = acc; memcpy(pp + acc, public_values + pv_off[i], len); acc += len;
-            }
-            po[m] = acc;
-            CK(cudaMemcpyAsync(c->d_in, c->h_pin, pv_at + pvb, cudaMemcpyHostToDevice, c->stream));
-            Job j; memset(&j, 0, sizeof j);
-            j.vk = vk; j.n = m; j.recs = c->d_in; j.stride = 256; j.off = 0; j.mode = SIG_SP1; j.sig_a = c->d_in + rb; j.sig_b = c->d_in + pv_at;
-            j.pv_off = (const uint64_t*)(c->d_in + rb + kb); j.base = c->h_ic0; j.d_status = c->d_out;
-            rc = run_verify(c, j); if (rc) return rc;
-            CK(cudaMemcpyAsync(c->h_out, c->d_out, m, cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaStreamSynchronize(c->stream));
-            collect_stage_ms(c);
+            // chunk block layout: [proofs cnt x 256][vkeys cnt x 32][offsets (cnt + 1) x 8][public values]
+            int rc = host_pipeline(c, m, m * (256 + 32 + 8) + 8 * 64 + pvb, 2,
+                [&](size_t first, size_t cnt, uint8_t* dst) -> size_t {
+                    uint8_t* pk = dst + cnt * 256; uint64_t* po = (uint64_t*)(pk + cnt * 32); uint8_t* pp = (uint8_t*)(po + cnt + 1);
+                    uint64_t acc = 0;
+                    for (size_t t = 0; t < cnt; t++) {
+                        size_t i = cand[s0 + first + t]; uint64_t len = pv_off[i + 1] - pv_off[i];
+                        memcpy(dst + t * 256, proofs + proof_off[i] + 4, 256); memcpy(pk + t * 32, vkeys + i * 32, 32);
+                        po[t] = acc; memcpy(pp + acc, public_values + pv_off[i], len); acc += len;
+                    }
+                    po[cnt] = acc;
+                    return cnt * (256 + 32) + (cnt + 1) * 8 + acc;
+                },
+                [&](size_t first, size_t cnt, uint8_t* d) -> Job {
+                    Job j; memset(&j, 0, sizeof j);
+                    j.vk = vk; j.n = cnt; j.recs = d; j.stride = 256; j.off = 0; j.mode = SIG_SP1; j.sig_a = d + cnt * 256;
+                    j.pv_off = (const uint64_t*)(d + cnt * 288); j.sig_b = d + cnt * 288 + (cnt + 1) * 8; j.base = c->h_ic0; j.d_status = c->d_out + first;
+                    return j;
+                });
+            if (rc) return rc;
             for (size_t t = 0; t < m; t++) status_out[cand[s0 + t]] = c->h_out[t];
         }
         return 0;
