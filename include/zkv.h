@@ -140,7 +140,8 @@ int zkv_vk_x_batch(const zkv_vk* vk, const uint8_t* signals, int k, size_t n, ui
 int zkv_fp_mul_batch(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out, int device);
 /* Fp12 tower operations of the pairing kernels on byte operands (n x 384 B = 12 x BE-32, tower order c0.c0.c0, c0.c0.c1, ...), for
  * parity tests against the oracle: op 0 a*b, 1 a^2, 2 a * line(l0,l3,l4) with the line in b's first three Fp2 slots, 3 cyclotomic
- * squaring, 4 inverse, 5/6/7 Frobenius^1/2/3, 8 final exponentiation.  b may be NULL for the unary operations. */
+ * squaring, 4 inverse, 5/6/7 Frobenius^1/2/3, 8 final exponentiation, 9 Miller loop of the single pair (P, Q) held in b's first six words (P.x, P.y, Q in
+ * wire order; a is ignored).  b may be NULL for the unary operations. */
 int zkv_fp12_op_batch(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out, int device);
 /* G2 membership kernel alone: out[i] = 1 in G2 / 0 on twist but wrong subgroup / 2 invalid encoding or off twist */
 int zkv_g2_check_batch(const uint8_t* g2s, size_t n, uint8_t* out, int device);

@@ -486,17 +486,25 @@ ZKV_HD ZKV_NOINLINE void g2_frob_affine(fp2& x, fp2& y, int k) {   // pi^k on af
     f2_mul(x, x, gx); f2_mul(y, y, gy);
 }
 // f *= line evaluated at the G1 point (px, py); with off != 0 the factor is replaced by 1 (a pair with a member at
-// infinity contributes 1, EIP-197) by redirecting the operands to constants: l0 * py -> 1 * 1, l3 * px -> 0, l4 -> 0.
-// Same instruction stream either way, so the block stays in lockstep.
-ZKV_HD ZKV_INLINE void f12_mul_line_at(fp12& f, const line_t& l, const fp& px, const fp& py, bool off) {
-    const fp2* one2 = (const fp2*)C_ONE2; const fp2* zero2 = (const fp2*)C_ZERO2;
-    const fp2* l0 = off ? one2 : &l.l0; const fp2* l3 = off ? zero2 : &l.l3; const fp2* l4 = off ? zero2 : &l.l4;
-    const fp* y = off ? &one2->c0 : &py;
-    fp2 a, b; f2_mul_fp(a, *l0, *y); f2_mul_fp(b, *l3, px);
-    f12_mul_line(f, a, b, *l4);
+// infinity contributes 1, EIP-197): the evaluated coefficients are overwritten with (1, 0, 0) by word-wise selects, so every
+// thread runs the same instruction stream and the block stays in lockstep.
+// OUT OF LINE ON PURPOSE (as are the Miller loops below).  nvcc 12.9's optimiser (cicc -O1 and up; -O0 is fine) merged the stack
+// slots of this routine's temporaries, when it was inlined into the Miller loop, with x2 / y2 of the loop's Frobenius tail, which are
+// still live: the second Frobenius line was then computed from clobbered operands and the Miller value of the variable pair came out
+// wrong, in some builds and not in others.  Routines with sizeable temporaries are therefore never inlined into a
+// frame that keeps its own values across the call, and the Frobenius operands are computed right before their single use.
+ZKV_HD ZKV_NOINLINE void f12_mul_line_at(fp12& f, const line_t& l, const fp& px, const fp& py, bool off) {
+    fp2 a, b, c;
+    f2_mul_fp(a, l.l0, py); f2_mul_fp(b, l.l3, px); c = l.l4;
+    const uint32_t keep = off ? 0u : 0xffffffffu;
+    for (int k = 0; k < 8; k++) {
+        a.c0.v[k] = (a.c0.v[k] & keep) | (C_ONE[k] & ~keep); a.c1.v[k] &= keep;
+        b.c0.v[k] &= keep; b.c1.v[k] &= keep; c.c0.v[k] &= keep; c.c1.v[k] &= keep;
+    }
+    f12_mul_line(f, a, b, c);
 }
 // all ZKV_LINES_PER_G2 lines of a fixed G2 point, in the order the Miller loop consumes them
-ZKV_HD inline void g2_precompute_lines(line_t* out, const fp2& qx, const fp2& qy) {
+ZKV_HD ZKV_NOINLINE void g2_precompute_lines(line_t* out, const fp2& qx, const fp2& qy) {
     g2j R; R.x = qx; R.y = qy; R.z = f2_one();
     int n = 0;
     for (int d = ZKV_ATE_NAF_LEN - 2; d >= 0; d--) {
@@ -504,16 +512,14 @@ ZKV_HD inline void g2_precompute_lines(line_t* out, const fp2& qx, const fp2& qy
         int dg = C_ATE_NAF[d];
         if (dg) { fp2 y = qy; if (dg < 0) f2_neg(y, y); line_add(R, qx, y, out[n++]); }
     }
-    fp2 x1 = qx, y1 = qy; g2_frob_affine(x1, y1, 1);
-    fp2 x2 = qx, y2 = qy; g2_frob_affine(x2, y2, 2); f2_neg(y2, y2);
-    line_add(R, x1, y1, out[n++]);
-    line_add(R, x2, y2, out[n++]);
+    { fp2 x1 = qx, y1 = qy; g2_frob_affine(x1, y1, 1); line_add(R, x1, y1, out[n++]); }
+    { fp2 x2 = qx, y2 = qy; g2_frob_affine(x2, y2, 2); f2_neg(y2, y2); line_add(R, x2, y2, out[n++]); }
 }
 
 // Multi-Miller loop: one variable G2 (qx,qy; pair 0) + nfixed tabled G2 points (pairs 1..nfixed).
 // skip bit j set => pair j contributes 1 (a member is infinity).  px/py: G1 points (Montgomery, affine).
 // Every thread executes every step (skipped pairs multiply by 1), so the control flow is uniform across a block.
-ZKV_HD inline void miller_loop(fp12& f, const fp* px, const fp* py, const fp2& qx, const fp2& qy,
+ZKV_HD ZKV_NOINLINE void miller_loop(fp12& f, const fp* px, const fp* py, const fp2& qx, const fp2& qy,
                                const line_t* const* tabs, int nfixed, uint32_t skip) {
     f = f12_one();
     g2j R; R.x = qx; R.y = qy; R.z = f2_one();
@@ -533,10 +539,10 @@ ZKV_HD inline void miller_loop(fp12& f, const fp* px, const fp* py, const fp2& q
             li++;
         }
     }
-    fp2 x1 = qx, y1 = qy; g2_frob_affine(x1, y1, 1);
-    fp2 x2 = qx, y2 = qy; g2_frob_affine(x2, y2, 2); f2_neg(y2, y2);
-    for (int s = 0; s < 2; s++) {
-        line_add(R, s ? x2 : x1, s ? y2 : y1, l); f12_mul_line_at(f, l, px[0], py[0], var_off);
+    for (int s = 1; s <= 2; s++) {                      // the two Frobenius lines: Q1 = pi(Q), Q2 = -pi^2(Q), each computed right before its use
+        fp2 xs = qx, ys = qy; g2_frob_affine(xs, ys, s);
+        if (s == 2) f2_neg(ys, ys);
+        line_add(R, xs, ys, l); f12_mul_line_at(f, l, px[0], py[0], var_off);
         for (int j = 0; j < nfixed; j++) f12_mul_line_at(f, tabs[j][li], px[j + 1], py[j + 1], ((skip >> (j + 1)) & 1u) != 0);
         li++;
     }

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_final_exp(int n, co
     if (gt_out) f12_to_bytes(gt_out + (size_t)i * 384, gt);
 }
 // parity hook: one Fp12 tower operation per thread on byte operands (12 x BE-32 each, tower order).
-// op 0: a*b  1: a^2  2: a * line(b.c0.c0, b.c0.c1, b.c0.c2)  3: cyclotomic square  4: 1/a  5..7: Frobenius^(op-4)  8: final exponentiation
+// op 0: a*b  1: a^2  2: a * line(b.c0.c0, b.c0.c1, b.c0.c2)  3: cyclotomic square  4: 1/a  5..7: Frobenius^(op-4)  8: final exponentiation  9: single-pair Miller loop
 __global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_fp12_op(int n, int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     int i0 = blockIdx.x * blockDim.x + threadIdx.x;
     int i = i0 < n ? i0 : n - 1;                      // every thread runs the operation: the tower routines contain block-wide rendezvous
@@ -244,7 +244,10 @@ __global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_fp12_op(int n, int 
         case 3: f12_cyc_sqr(z, x); break;
         case 4: f12_inv(z, x); break;
         case 5: case 6: case 7: f12_frob(z, x, op - 4); break;
-        default: final_exp(z, x); break;
+        case 8: final_exp(z, x); break;
+        default: {                                    // op 9: Miller loop of one pair (P, Q) with a variable Q; b holds P.x, P.y, Q in wire order (x_im, x_re, y_im, y_re)
+            fp px[1] = {yw[0]}, py[1] = {yw[1]}; fp2 qx, qy; qx.c1 = yw[2]; qx.c0 = yw[3]; qy.c1 = yw[4]; qy.c0 = yw[5];
+            miller_loop(z, px, py, qx, qy, nullptr, 0, n > (1 << 30) ? 1u : 0u); break; }
     }
     if (i0 < n) f12_to_bytes(out + (size_t)i * 384, z);
 }

@@ -709,7 +709,7 @@ extern "C" int zkv_fp_mul_batch(const uint8_t* a, const uint8_t* b, size_t n, ui
     return with_scratch(device, a, n * 32, b, n * 32, out, n * 32, &dummy, 0, [&](uint8_t* d0, uint8_t* d1, uint8_t* o0, uint8_t*) { k_fp_mul_bytes<<<nblk(n), TPB>>>((int)n, d0, d1, o0); });
 }
 extern "C" int zkv_fp12_op_batch(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out, int device) {
-    if (!a || !out || op < 0 || op > 8 || ((op == 0 || op == 2) && !b)) return fail(ZKV_ERR_ARG, "zkv_fp12_op_batch: bad argument");
+    if (!a || !out || op < 0 || op > 9 || ((op == 0 || op == 2 || op == 9) && !b)) return fail(ZKV_ERR_ARG, "zkv_fp12_op_batch: bad argument");
     if (n == 0) return 0;
     uint8_t dummy;
     return with_scratch(device, a, n * 384, b ? b : &dummy, b ? n * 384 : 0, out, n * 384, &dummy, 0,

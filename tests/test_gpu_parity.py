@@ -77,6 +77,17 @@ def test_fp12_tower_ops(Z):
         assert cs[384 * i:384 * i + 384] == O.fp12_cyc_sqr(g) == O.fp12_mul(g, g), ("cyc_sqr", i)
 
 
+def test_single_pair_miller_loop_hook(Z, gpu):
+    """Miller loop of one (P, Q) pair with a variable Q, bit-exact against the oracle (the variable-pair code path on its own: doubling
+    and addition steps on the fly plus the two Frobenius lines; this is the path a compiler stack-slot bug once broke)."""
+    ks = [(5, 9), (77, 31), (12345, 999), (R - 1, 2), (3, R - 2)]
+    ps = gpu.g1_mul([k for k, _ in ks]); qs = gpu.g2_mul([k for _, k in ks])
+    n = len(ks)
+    got = Z.fp12_op_batch(9, bytes(384 * n), b"".join(p + q + bytes(192) for p, q in zip(ps, qs)), n)
+    for i, (p, q) in enumerate(zip(ps, qs)):
+        assert got[384 * i:384 * i + 384] == O.ec_pairing(p + q, debug=True)[1], i
+
+
 def test_ec_add_mul_services(Z):
     from stylus_zkvm_verifiers_b200.synth import SplitMix64
     rng = SplitMix64(2)
