@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--shape", default="risc0", choices=["risc0", "sp1"])
     ap.add_argument("--n", type=int, default=1 << 16, help="proofs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exact-lines", action="store_true", help="verification path with the unscaled gamma / delta lines (A/B measurement)")
     ap.add_argument("--chunks", type=int, default=0, help="stream-overlap chunks per device batch (0 = library default)")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
@@ -227,6 +228,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.exact_lines:
+        Z.set_normalised_lines(0)
     if args.chunks:
         Z.set_overlap(args.chunks)
     chunks = Z.set_overlap(0)                    # 0 is out of range: reads the current value

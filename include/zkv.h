@@ -152,6 +152,10 @@ int zkv_last_stage_ms(const void* handle_vk, int device, float* out, int cap);
  * one kernel is back-filled by blocks of another (default 2; batches under 8192 proofs are never cut).  chunks = 1 runs one chain on the
  * main stream and records the per-stage events zkv_last_stage_ms reads.  Process-wide; returns the previous value. */
 int zkv_set_overlap(int chunks);
+/* Verification path only: use the per-key normalised gamma / delta line tables (lines scaled by a subfield element so that their first
+ * coefficient is 1; the final exponentiation output and every status byte are unchanged).  On by default; 0 runs
+ * the unscaled lines of the pairing service instead (A/B measurements, parity tests).  Returns the previous setting. */
+int zkv_set_normalised_lines(int on);
 /* integer-pipe microbenchmark (roofline denominator): returns measured IMAD.WIDE.U32 results/s and
  * Fp-multiplications/s on `device` */
 int zkv_imad_peak(int device, double* wide_per_s, double* fpmul_per_s);

@@ -548,6 +548,82 @@ ZKV_HD ZKV_NOINLINE void miller_loop(fp12& f, const fp* px, const fp* py, const 
     }
 }
 
+// ------------------------------------------------------------------------------------------ normalised lines (verify path)
+// A line of a FIXED G2 point evaluated at P = (xP, yP) is  l0 yP + l3 xP w + l4 v w.  Dividing it by l0 yP (an element of Fp2: the final
+// exponentiation maps every element of a proper subfield to 1) leaves  1 + n3 (xP/yP) w + n4 (1/yP) v w  with n3 = l3/l0, n4 = l4/l0
+// tabulated per key.  The product of f with such a line needs 10 Fp2 multiplications instead of 13, and a pair that must contribute 1
+// (a member at infinity) is obtained by zeroing xP/yP and 1/yP: same instruction stream, no special case.
+// The Miller VALUE differs from the oracle's by subfield factors, the final exponentiation output (and so every accept / reject bit) does
+// not; this path is therefore used by the verification entry points only, never by the pairing service that exposes Miller values.
+struct nline_t { fp2 n3, n4; };
+// f *= 1 + (c3 + c4 v) w
+ZKV_HD ZKV_NOINLINE void f12_mul_line1(fp12& f, const fp2& c3, const fp2& c4) {
+    ZKV_RENDEZVOUS1();
+    fp6 a, b;
+    f6_mul_01(a, f.c1, c3, c4); f6_mul_01(b, f.c0, c3, c4);
+    f6_mul_v(a, a); f6_add(f.c0, f.c0, a); f6_add(f.c1, f.c1, b);
+}
+ZKV_HD ZKV_NOINLINE void f12_mul_nline_at(fp12& f, const nline_t& l, const fp& xy, const fp& iy) {
+    fp2 c3, c4; f2_mul_fp(c3, l.n3, xy); f2_mul_fp(c4, l.n4, iy);
+    f12_mul_line1(f, c3, c4);
+}
+// normalise a line table; returns false if some l0 is zero (degenerate key: the caller keeps the unscaled path)
+ZKV_HD ZKV_NOINLINE bool g2_normalise_lines(nline_t* out, const line_t* in, int n) {
+    // simultaneous inversion of all l0 (Montgomery's trick): out[i].n3 temporarily holds the prefix product l0_0 ... l0_i
+    fp2 acc = f2_one(); bool ok = true;
+    for (int i = 0; i < n; i++) { fp2 l0 = in[i].l0; if (f2_is_zero(l0)) ok = false; f2_mul(acc, acc, l0); out[i].n3 = acc; }
+    if (!ok) return false;
+    fp2 inv; f2_inv(inv, acc);
+    for (int i = n - 1; i >= 0; i--) {
+        fp2 li, l0 = in[i].l0, l3 = in[i].l3, l4 = in[i].l4, n3, n4;     // 1 / l0_i = inv(prefix_i) * prefix_{i-1}
+        if (i) { fp2 prev = out[i - 1].n3; f2_mul(li, inv, prev); } else li = inv;
+        f2_mul(inv, inv, l0);
+        f2_mul(n3, l3, li); f2_mul(n4, l4, li);
+        out[i].n3 = n3; out[i].n4 = n4;
+    }
+    return true;
+}
+// Verification-path Miller loop: pair 0 = (P0, variable Q), pairs 1, 2 = (P1, P2) against the normalised tables nt[0], nt[1].
+// xy[j] = xPj / yPj, iy[j] = 1 / yPj for the two fixed pairs (both zero for a pair that must contribute 1).
+ZKV_HD ZKV_NOINLINE void miller_loop_norm(fp12& f, const fp& px0, const fp& py0, const fp2& qx, const fp2& qy,
+                                          const nline_t* const* nt, const fp* xy, const fp* iy, bool var_off) {
+    f = f12_one();
+    g2j R; R.x = qx; R.y = qy; R.z = f2_one();
+    line_t l; int li = 0;
+    for (int d = ZKV_ATE_NAF_LEN - 2; d >= 0; d--) {
+        ZKV_RENDEZVOUS();
+        if (d != ZKV_ATE_NAF_LEN - 2) f12_sqr(f, f);
+        line_dbl(R, l); f12_mul_line_at(f, l, px0, py0, var_off);
+        for (int j = 0; j < 2; j++) f12_mul_nline_at(f, nt[j][li], xy[j], iy[j]);
+        li++;
+        int dg = C_ATE_NAF[d];
+        if (dg) {
+            fp2 y = qy; if (dg < 0) f2_neg(y, y);
+            line_add(R, qx, y, l); f12_mul_line_at(f, l, px0, py0, var_off);
+            for (int j = 0; j < 2; j++) f12_mul_nline_at(f, nt[j][li], xy[j], iy[j]);
+            li++;
+        }
+    }
+    for (int s = 1; s <= 2; s++) {
+        fp2 xs = qx, ys = qy; g2_frob_affine(xs, ys, s);
+        if (s == 2) f2_neg(ys, ys);
+        line_add(R, xs, ys, l); f12_mul_line_at(f, l, px0, py0, var_off);
+        for (int j = 0; j < 2; j++) f12_mul_nline_at(f, nt[j][li], xy[j], iy[j]);
+        li++;
+    }
+}
+// xy = x / y, iy = 1 / y for two affine G1 points with ONE inversion; a point with off set (or y == 0, which no point of the curve has)
+// gets xy = iy = 0
+ZKV_HD ZKV_NOINLINE void g1_slopes2(fp* xy, fp* iy, const fp* x, const fp* y, const bool* off) {
+    const bool o0 = off[0] || fp_is_zero(y[0]), o1 = off[1] || fp_is_zero(y[1]);
+    fp one = fp_one(), z = fp_zero(), y0 = o0 ? one : y[0], y1 = o1 ? one : y[1];
+    fp t, inv; fp_mul(t, y0, y1); fp_inv(inv, t);
+    fp i0, i1; fp_mul(i0, inv, y1); fp_mul(i1, inv, y0);
+    fp a0, a1; fp_mul(a0, x[0], i0); fp_mul(a1, x[1], i1);
+    xy[0] = o0 ? z : a0; xy[1] = o1 ? z : a1;
+    iy[0] = o0 ? z : i0; iy[1] = o1 ? z : i1;
+}
+
 // ------------------------------------------------------------------------------------------ byte <-> field
 ZKV_HD ZKV_INLINE void be32_to_raw(uint32_t* v, const uint8_t* b) {   // 32-byte big-endian -> 8 LE limbs (no reduction)
     for (int i = 0; i < 8; i++) { const uint8_t* q = b + 4 * (7 - i); v[i] = (uint32_t)q[0] << 24 | (uint32_t)q[1] << 16 | (uint32_t)q[2] << 8 | q[3]; }

@@ -181,6 +181,7 @@ struct MillerArgs {
     const fp2* qx; const fp2* qy;
     const line_t* tabs[3];
     int nfixed;
+    const nline_t* ntabs[2];  // verification path: normalised tables of gamma and delta (bn254.cuh), used by k_miller_norm
     const fp12* pre;
     uint8_t skip_bit[4];      // which flag bit disables pair j (0 = never)
     uint8_t vk_skip;          // pairs disabled for the whole batch (a vk G2 point at infinity)
@@ -206,6 +207,26 @@ __global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_miller(int n, Mille
     fp2 qx = a.qx[i], qy = a.qy[i];
     fp12 f;
     miller_loop(f, px, py, qx, qy, a.tabs, a.nfixed, skip);
+    if (a.pre) { fp12 p = *a.pre; f12_mul(f, f, p); }
+    if (i0 < n) out[i] = f;
+}
+
+// K6 for the verification entry points: pairs (A', B), (vk_x, gamma), (C, delta) with the NORMALISED gamma / delta tables (bn254.cuh),
+// times the per-key constant Miller(alpha, beta).  Same launch shape and flag conventions as k_miller.
+__global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_miller_norm(int n, MillerArgs a, const uint8_t* flags, fp12* out) {
+    int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = i0 < n ? i0 : n - 1;
+    uint8_t fl = flags[i];
+    uint32_t skip = a.vk_skip;
+    for (int j = 0; j < 3; j++) if (fl & a.skip_bit[j]) skip |= 1u << j;
+    if (fl & (F_INVALID | F_SELMIS)) skip = 0xF;
+    fp x12[2] = {a.px[1][i], a.px[2][i]}, y12[2] = {a.py[1][i], a.py[2][i]}, xy[2], iy[2];
+    bool off[2] = {(skip & 2u) != 0, (skip & 4u) != 0};
+    g1_slopes2(xy, iy, x12, y12, off);
+    fp px0 = a.px[0][i], py0 = a.py[0][i];
+    fp2 qx = a.qx[i], qy = a.qy[i];
+    fp12 f;
+    miller_loop_norm(f, px0, py0, qx, qy, a.ntabs, xy, iy, (skip & 1u) != 0);
     if (a.pre) { fp12 p = *a.pre; f12_mul(f, f, p); }
     if (i0 < n) out[i] = f;
 }
@@ -262,9 +283,10 @@ struct VkDev {                 // device-resident, Montgomery form
     fp alpha_x, alpha_y;
     int valid;                 // all key points decode under EIP-196/197 rules (else every verify fails)
     int g2_inf[3]; int alpha_inf;
+    int norm_ok;               // the normalised gamma / delta line tables exist (no vanishing l0)
 };
 // block j<3 (one thread each) validates + tabulates G2 point j; block 3 validates alpha
-__global__ void k_vk_setup(const uint8_t* alpha, const uint8_t* g2bytes /* 3 x 128 */, VkDev* vk, line_t* lines /* 3 x LINES */) {
+__global__ void k_vk_setup(const uint8_t* alpha, const uint8_t* g2bytes /* 3 x 128 */, VkDev* vk, line_t* lines /* 3 x LINES */, nline_t* nlines /* 2 x LINES: gamma, delta */) {
     int j = blockIdx.x;
     if (j < 3) {
         fp2 x, y;
@@ -273,6 +295,7 @@ __global__ void k_vk_setup(const uint8_t* alpha, const uint8_t* g2bytes /* 3 x 1
         vk->g2x[j] = x; vk->g2y[j] = y; vk->g2_inf[j] = (r == 1);
         if (r == 2) atomicAnd(&vk->valid, 0);
         if (r == 0) g2_precompute_lines(lines + (size_t)j * ZKV_LINES_PER_G2, x, y);
+        if (j >= 1 && (r != 0 || !g2_normalise_lines(nlines + (size_t)(j - 1) * ZKV_LINES_PER_G2, lines + (size_t)j * ZKV_LINES_PER_G2, ZKV_LINES_PER_G2))) atomicAnd(&vk->norm_ok, 0);
     } else if (j == 3) {
         uint32_t rx[8], ry[8]; be32_to_raw(rx, alpha); be32_to_raw(ry, alpha + 32);
         fp x, y; int r = g1_decode_raw(x, y, rx, ry);

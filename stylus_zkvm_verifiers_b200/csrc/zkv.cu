@@ -56,7 +56,7 @@ struct DevCtx {
     int device = 0;
     cudaStream_t stream = nullptr;
     // per-vk tables (device memory, Montgomery form)
-    VkDev* d_vk = nullptr; line_t* d_lines = nullptr; fp12* d_pre = nullptr; g1aff* d_tab = nullptr; g1aff* d_ic0 = nullptr;
+    VkDev* d_vk = nullptr; line_t* d_lines = nullptr; nline_t* d_nlines = nullptr; fp12* d_pre = nullptr; g1aff* d_tab = nullptr; g1aff* d_ic0 = nullptr;
     VkDev h_vk; g1aff h_ic0;
     // workspace
     size_t cap = 0;
@@ -102,7 +102,7 @@ static void ctx_free(DevCtx* c) {
     for (int j = 0; j < 4; j++) { cudaFree(c->px[j]); cudaFree(c->py[j]); }
     cudaFree(c->qx); cudaFree(c->qy); cudaFree(c->f); cudaFree(c->flags); cudaFree(c->status); cudaFree(c->scal);
     cudaFree(c->d_in); cudaFree(c->d_out); cudaFreeHost(c->h_pin); cudaFreeHost(c->h_out);
-    cudaFree(c->d_vk); cudaFree(c->d_lines); cudaFree(c->d_pre); cudaFree(c->d_tab); cudaFree(c->d_ic0);
+    cudaFree(c->d_vk); cudaFree(c->d_lines); cudaFree(c->d_nlines); cudaFree(c->d_pre); cudaFree(c->d_tab); cudaFree(c->d_ic0);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_join) if (e) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -129,7 +129,7 @@ static int vk_build_on(zkv_vk* vk, DevCtx* c) {
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     for (auto& e : c->ev_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     int nt = vk->n_ic - 1;
-    CK(cudaMalloc(&c->d_vk, sizeof(VkDev))); CK(cudaMalloc(&c->d_lines, sizeof(line_t) * 3 * ZKV_LINES_PER_G2)); CK(cudaMalloc(&c->d_pre, sizeof(fp12)));
+    CK(cudaMalloc(&c->d_vk, sizeof(VkDev))); CK(cudaMalloc(&c->d_lines, sizeof(line_t) * 3 * ZKV_LINES_PER_G2)); CK(cudaMalloc(&c->d_nlines, sizeof(nline_t) * 2 * ZKV_LINES_PER_G2)); CK(cudaMalloc(&c->d_pre, sizeof(fp12)));
     CK(cudaMalloc(&c->d_tab, sizeof(g1aff) * (size_t)nt * ZKV_WIN_PER_SCALAR * ZKV_WIN_ENTRIES)); CK(cudaMalloc(&c->d_ic0, sizeof(g1aff)));
     uint8_t* d_bytes; size_t nb = 64 + 384 + vk->ic.size();
     CK(cudaMalloc(&d_bytes, nb));
@@ -137,10 +137,11 @@ static int vk_build_on(zkv_vk* vk, DevCtx* c) {
     memcpy(hb.data(), vk->alpha, 64); memcpy(hb.data() + 64, vk->beta, 128); memcpy(hb.data() + 192, vk->gamma, 128); memcpy(hb.data() + 320, vk->delta, 128);
     memcpy(hb.data() + 448, vk->ic.data(), vk->ic.size());
     CK(cudaMemcpyAsync(d_bytes, hb.data(), nb, cudaMemcpyHostToDevice, c->stream));
-    VkDev init; memset(&init, 0, sizeof init); init.valid = 1;
+    VkDev init; memset(&init, 0, sizeof init); init.valid = 1; init.norm_ok = 1;
     CK(cudaMemcpyAsync(c->d_vk, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemsetAsync(c->d_lines, 0, sizeof(line_t) * 3 * ZKV_LINES_PER_G2, c->stream));
-    k_vk_setup<<<4, 1, 0, c->stream>>>(d_bytes, d_bytes + 64, c->d_vk, c->d_lines);
+    CK(cudaMemsetAsync(c->d_nlines, 0, sizeof(nline_t) * 2 * ZKV_LINES_PER_G2, c->stream));
+    k_vk_setup<<<4, 1, 0, c->stream>>>(d_bytes, d_bytes + 64, c->d_vk, c->d_lines, c->d_nlines);
     k_ic_tables<<<nt, ZKV_WIN_PER_SCALAR, 0, c->stream>>>(d_bytes + 448, c->d_tab, c->d_ic0, c->d_vk);
     k_vk_miller_ab<<<1, 1, 0, c->stream>>>(c->d_vk, c->d_lines, c->d_pre);
     CK(cudaGetLastError());
@@ -206,6 +207,8 @@ __global__ void k_status_all_fail(int n, const uint8_t* flags, uint8_t* status) 
 }
 // Number of chunks a device batch is cut into (each chunk's kernel chain runs on its own side stream).  1 = one chain on the main stream
 // with per-stage events (what bench.py uses for the per-kernel roofline figures).
+static int g_normalised_lines = 1;      // verification path: gamma / delta lines scaled to (1, n3, n4): 10 instead of 13 Fp2 multiplications per line
+extern "C" int zkv_set_normalised_lines(int on) { int old = g_normalised_lines; if (on == 0 || on == 1) g_normalised_lines = on; return old; }
 static int g_overlap_chunks = 2;
 extern "C" int zkv_set_overlap(int chunks) { int old = g_overlap_chunks; if (chunks >= 1 && chunks <= 64) g_overlap_chunks = chunks; return old; }
 
@@ -242,9 +245,12 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
     a.qx = c->qx + o; a.qy = c->qy + o;
     a.tabs[0] = c->d_lines + 1 * ZKV_LINES_PER_G2; a.tabs[1] = c->d_lines + 2 * ZKV_LINES_PER_G2;
     a.nfixed = 2; a.pre = c->d_pre;
+    a.ntabs[0] = c->d_nlines; a.ntabs[1] = c->d_nlines + ZKV_LINES_PER_G2;
+    const bool norm = c->h_vk.norm_ok && g_normalised_lines;
     a.skip_bit[0] = F_SKIP0; a.skip_bit[1] = F_SKIPX; a.skip_bit[2] = F_SKIPC;
     a.vk_skip = (uint8_t)((c->h_vk.g2_inf[1] ? 2 : 0) | (c->h_vk.g2_inf[2] ? 4 : 0));
-    k_miller<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, a, flags, c->f + o);
+    if (norm) k_miller_norm<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, a, flags, c->f + o);
+    else k_miller<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, a, flags, c->f + o);
     if (timed) CK(cudaEventRecord(c->ev[4], s));
     k_final_exp<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, c->f + o, flags, j.d_status + jo, nullptr, 0);
     if (timed) CK(cudaEventRecord(c->ev[5], s));

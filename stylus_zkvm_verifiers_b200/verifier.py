@@ -301,6 +301,11 @@ def set_overlap(chunks):
     return N.lib().zkv_set_overlap(int(chunks))
 
 
+def set_normalised_lines(on):
+    """Verification path: normalised gamma / delta line tables on (default) or off; returns the previous setting."""
+    return N.lib().zkv_set_normalised_lines(int(on))
+
+
 def imad_peak(device=0):
     w, f = C.c_double(0), C.c_double(0)
     N.check(N.lib().zkv_imad_peak(device, C.byref(w), C.byref(f)))

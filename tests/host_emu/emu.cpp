@@ -48,6 +48,27 @@ int emu_pairing3_pre(const uint8_t* g1s /*4x64: A, alpha, vkx, C*/, const uint8_
     f12_to_bytes(miller_out, f);
     return 0;
 }
+// the verification path as run_verify does it: normalised gamma / delta tables, 3-pair loop, times Miller(alpha, beta), final exponentiation
+int emu_verify_norm_gt(const uint8_t* g1s /*4x64: A, alpha, vkx, C*/, const uint8_t* g2, const uint8_t* fixed, int skip_mask, uint8_t* gt_out) {
+    static line_t tabs_store[3][ZKV_LINES_PER_G2];
+    static nline_t ntabs[2][ZKV_LINES_PER_G2];
+    fp px[4], py[4];
+    for (int j = 0; j < 4; j++) { dec_fp(px[j], g1s + 64 * j); dec_fp(py[j], g1s + 64 * j + 32); }
+    fp2 qx, qy; dec_g2(qx, qy, g2);
+    for (int j = 0; j < 3; j++) { fp2 x, y; dec_g2(x, y, fixed + 128 * j); g2_precompute_lines(tabs_store[j], x, y); }
+    for (int j = 0; j < 2; j++) if (!g2_normalise_lines(ntabs[j], tabs_store[j + 1], ZKV_LINES_PER_G2)) return -1;
+    fp12 pre, f, gt;
+    { fp ax[2] = {fp_zero(), px[1]}, ay[2] = {fp_zero(), py[1]}; const line_t* t1[1] = {tabs_store[0]}; fp2 z = f2_zero(); miller_loop(pre, ax, ay, z, z, t1, 1, 1u); }
+    fp x2[2] = {px[2], px[3]}, y2[2] = {py[2], py[3]}, xy[2], iy[2];
+    bool off[2] = {(skip_mask & 2) != 0, (skip_mask & 4) != 0};
+    g1_slopes2(xy, iy, x2, y2, off);
+    const nline_t* nt[2] = {ntabs[0], ntabs[1]};
+    miller_loop_norm(f, px[0], py[0], qx, qy, nt, xy, iy, (skip_mask & 1) != 0);
+    f12_mul(f, f, pre);
+    final_exp(gt, f);
+    f12_to_bytes(gt_out, gt);
+    return f12_is_one(gt) ? 1 : 0;
+}
 // scalar multiple by double-and-add with the complete mixed addition used by k_vkx / k_ec_mul
 int emu_g1_mul(const uint8_t* pt, const uint8_t* k, uint8_t* out) {
     fp x, y; dec_fp(x, pt); dec_fp(y, pt + 32);

@@ -255,6 +255,29 @@ def test_risc0_shape_mixed_batch_vs_oracle(Z, gpu, fx, seed):
     assert len(set(got)) >= 4          # OK, INVALID_PROOF_DATA, SELECTOR_MISMATCH, VERIFICATION_FAILED all occur
 
 
+def test_normalised_and_unscaled_lines_agree(Z, gpu, fx):
+    """The verification path scales the gamma / delta lines by subfield elements (10 instead of 13 Fp2 products per line): every status
+    byte must equal both the oracle's and the one obtained with the unscaled lines of the pairing service."""
+    from stylus_zkvm_verifiers_b200 import synth as S
+    vk = S.make_vk(gpu, 0, 6, 0xB2000009)
+    kv = Z.VerificationKey(0, vk.alpha, vk.beta, vk.gamma, vk.delta, vk.ic)
+    v = Z.RiscZeroVerifier(kv); v.initialize(fx["control_root"], fx["bn254_control_id"])
+    n = 300
+    batch = S.make_risc0_batch(gpu, vk, v.get_selector(), fx["control_root"], fx["bn254_control_id"], fx["sys0"], n, 0xB2000009, pool=32)
+    S.mutate_risc0(batch, gpu, S.SplitMix64(0xB200000A))
+    ro = O.Risc0Oracle(oracle_vk(vk)); ro.initialize(fx["control_root"], fx["bn254_control_id"])
+    want = ro.verify_batch(batch.seals, batch.image_ids, batch.journals)
+    prev = Z.set_normalised_lines(1)
+    try:
+        a = v.verify_batch(batch.seals, batch.image_ids, batch.journals)
+        Z.set_normalised_lines(0)
+        b = v.verify_batch(batch.seals, batch.image_ids, batch.journals)
+    finally:
+        Z.set_normalised_lines(prev)
+    assert a.tolist() == want.tolist() and b.tolist() == want.tolist()
+    assert 0 < int((want == 0).sum()) < n
+
+
 def test_sp1_shape_mixed_batch_vs_oracle(Z, gpu):
     from stylus_zkvm_verifiers_b200 import synth as S
     vk = S.make_vk(gpu, 1, 3, 0xB2000003)

@@ -100,6 +100,14 @@ def test_pairing_values_bit_exact(emu, consts):
         assert mo.raw == m and go.raw == gt and ok == ret[31]
         emu.emu_pairing3_pre(g1s, q, fixed, m3)                        # 3-pair loop x precomputed Miller(alpha, beta): same field element
         assert m3.raw == m
+        # verification path (normalised gamma / delta lines): different Miller value, the SAME final-exponentiation output
+        assert emu.emu_verify_norm_gt(g1s, q, fixed, 0, go) == ret[31] and go.raw == gt
+        # pairs switched off (a member at infinity contributes 1): compare with the oracle on the remaining pairs
+        for mask, keep in ((2, (0, 1, 3)), (4, (0, 1, 2)), (1, (1, 2, 3)), (6, (0, 1))):
+            g2s = (q, fixed[0:128], fixed[128:256], fixed[256:384])
+            d2 = b"".join(g1s[64 * j:64 * j + 64] + g2s[j] for j in keep)
+            r2, _, gt2 = O.ec_pairing(d2, debug=True)
+            assert emu.emu_verify_norm_gt(g1s, q, fixed, mask, go) == r2[31] and go.raw == gt2, mask
 
 
 def test_g1_scalar_mul(emu):
