@@ -37,7 +37,7 @@ def ncu_traffic(kernel):
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))
         for k in d["kernels"]:
-            if k["kernel"] == kernel:
+            if k["kernel"] == kernel and "source_page" in k:
                 return {"bytes_per_launch": k["dram_bytes_read"] + k["dram_bytes_write"], "proofs_per_launch": k["proofs"], "source": "profiles/r1_ncu_summary.json"}
     except Exception:
         pass
@@ -285,6 +285,7 @@ def main():
     miller_ms = stage_sum.get("miller", 0.0)
     fe_ms = stage_sum.get("final_exp", 0.0)
     mac_miller = n * W_MILLER3_M * M_MAC32
+    miller_kernel = "k_miller" if args.exact_lines else "k_miller_norm"    # verification path: normalised gamma / delta lines by default
     line = {
         "metric": "groth16_verifies_per_sec", "value": value, "unit": "verifies/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -296,8 +297,8 @@ def main():
         "e2e": {"value": total / e2e_s, "unit": "verifies/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": n},
         "gpu_launches": 6 * (chunks if n >= 8192 else 1) * args.steps,
         "stage_ms": stage_sum,
-        "roofline": {"bound": "imad", "bound_note": "integer-multiply (IMAD.WIDE) issue rate; neither HBM nor the tensor cores bound this path (SURVEY 8d)", "kernel": "k_miller", "achieved": mac_miller / (miller_ms * 1e-3) / 1e12 if miller_ms else None, "peak": imad_peak / 1e12,
-                     "unit": "TMAC32/s", "frac": (mac_miller / (miller_ms * 1e-3)) / imad_peak if miller_ms else None, "traffic": ncu_traffic("k_miller"),
+        "roofline": {"bound": "imad", "bound_note": "integer-multiply (IMAD.WIDE) issue rate; neither HBM nor the tensor cores bound this path (SURVEY 8d)", "kernel": miller_kernel, "achieved": mac_miller / (miller_ms * 1e-3) / 1e12 if miller_ms else None, "peak": imad_peak / 1e12,
+                     "unit": "TMAC32/s", "frac": (mac_miller / (miller_ms * 1e-3)) / imad_peak if miller_ms else None, "traffic": ncu_traffic(miller_kernel),
                      "peak_source": "IMAD.WIDE.U32 issue rate measured live on this GPU (zkv_imad_peak); MEASURED_PEAKS.json holds no integer figure",
                      "fpmul_chain_per_s": fpmul_peak,
                      "whole_path_frac": value / world * W_M * M_MAC32 / imad_peak,

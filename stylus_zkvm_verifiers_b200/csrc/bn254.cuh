@@ -412,6 +412,24 @@ ZKV_HD ZKV_NOINLINE void g2_add(g2j& r, const g2j& p, const g2j& q) {   // compl
     f2_mul(z3, p.z, q.z); f2_mul(z3, z3, h);
     r.x = x3; r.y = y3; r.z = z3;
 }
+// r = p + (qx, qy) with the second point affine (8 M + 3 S instead of 12 M + 4 S); complete like g2_add
+ZKV_HD ZKV_NOINLINE void g2_add_affine(g2j& r, const g2j& p, const fp2& qx, const fp2& qy) {
+    if (f2_is_zero(p.z)) { r.x = qx; r.y = qy; r.z = f2_one(); return; }
+    fp2 z1z1, u2, s2, h, rr, t, hh, hhh, v, x3, y3, z3;
+    f2_sqr(z1z1, p.z); f2_mul(u2, qx, z1z1);
+    f2_mul(s2, qy, p.z); f2_mul(s2, s2, z1z1);
+    f2_sub(h, u2, p.x); f2_sub(rr, s2, p.y);
+    if (f2_is_zero(h)) {
+        if (f2_is_zero(rr)) { g2_dbl(r, p); }
+        else { r.x = f2_one(); r.y = f2_one(); r.z = f2_zero(); }
+        return;
+    }
+    f2_sqr(hh, h); f2_mul(hhh, hh, h); f2_mul(v, p.x, hh);
+    f2_sqr(x3, rr); f2_sub(x3, x3, hhh); f2_dbl(t, v); f2_sub(x3, x3, t);
+    f2_sub(t, v, x3); f2_mul(y3, rr, t); f2_mul(t, p.y, hhh); f2_sub(y3, y3, t);
+    f2_mul(z3, p.z, h);
+    r.x = x3; r.y = y3; r.z = z3;
+}
 // psi^k = twist o Frobenius^k o untwist, on Jacobian coordinates
 ZKV_HD ZKV_INLINE void g2_psi(g2j& r, const g2j& p, int k) {
     fp2 x = p.x, y = p.y, z = p.z;
@@ -432,10 +450,13 @@ ZKV_HD ZKV_INLINE bool g2j_eq(const g2j& a, const g2j& b) {
 // which is what tests/ check on subgroup, wrong-subgroup and small-order twist points.
 ZKV_HD ZKV_NOINLINE bool g2_in_subgroup(const fp2& qx, const fp2& qy) {
     g2j q; q.x = qx; q.y = qy; q.z = f2_one();
-    g2j uq = q;
-    for (int i = 61; i >= 0; i--) {
+    fp2 ax = qx, ay = qy, ny; f2_neg(ny, ay);
+    g2j uq = q;                                      // [u]Q by the NAF of u with mixed additions of +-Q
+    for (int i = ZKV_U_NAF_LEN - 2; i >= 0; i--) {
         g2j t; g2_dbl(t, uq); uq = t;
-        if ((ZKV_BN_U >> i) & 1) { g2_add(t, uq, q); uq = t; }
+        const int d = C_U_NAF[i];
+        if (d > 0) { g2_add_affine(t, uq, ax, ay); uq = t; }
+        else if (d < 0) { g2_add_affine(t, uq, ax, ny); uq = t; }
     }
     g2j lhs, t, p1, p2, p3;
     g2_add(lhs, uq, q);

@@ -53,7 +53,7 @@ def main(out, reps):
             for key, col in (("dram_bytes_read", "dram__bytes_read.sum"), ("dram_bytes_write", "dram__bytes_write.sum")):
                 d[key] = float(r[ix[col]].replace(",", "")) * SCALE.get(units[ix[col]], 1)
             d["proofs"] = int(d.get("launch__grid_size", 0) * d.get("launch__block_size", 0))
-            if name in ("k_miller", "k_final_exp"):
+            if name in ("k_miller", "k_miller_norm", "k_final_exp") and d["proofs"] >= 1024:
                 d["source_page"] = source_mix(rep, name)
             kernels.append(d)
     json.dump({"source": "ncu --set full --import-source on --clock-control none ... python bench.py --steps 1 --warmup 3 --no-cpu-baseline --chunks 1 (2^16 RISC Zero-shape proofs, "
