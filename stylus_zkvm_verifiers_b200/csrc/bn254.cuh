@@ -301,44 +301,40 @@ ZKV_HD ZKV_NOINLINE void f12_cyc_sqr(fp12& r, const fp12& a) {
     f2_add(x, t3, z5); f2_dbl(x, x); f2_add(r.c1.c2, x, t3);     // 3 t3 + 2 z5
 }
 // a^u for a in the cyclotomic subgroup, by the width-3 NAF of u (digits 0, +-1, +-3): one cyclotomic squaring per digit, one
-// multiplication per non-zero digit (17 instead of the 27 of the binary expansion the oracle uses; same value).  A negative digit
-// multiplies by the inverse, which for a unitary element is the conjugate: the two table entries are conjugated in place when the
-// sign they are needed with changes.
+// multiplication per non-zero digit (18 instead of the 27 of the binary expansion the oracle uses; same value).  A negative digit
+// multiplies by the inverse, which for a unitary element is the conjugate: acc * conj(x) = conj(conj(acc) * x), so the table (a, a^3)
+// is never modified and the input needs no copy.  r must not alias a.
 ZKV_HD ZKV_NOINLINE void f12_pow_u(fp12& r, const fp12& a) {
-    fp12 a1 = a, a3, acc;
-    f12_cyc_sqr(acc, a1); f12_mul(a3, acc, a1);
-    bool neg1 = false, neg3 = false;
-    if (C_U_WNAF3[ZKV_U_WNAF3_LEN - 1] == 1) acc = a1; else acc = a3;
+    fp12 a3;
+    f12_cyc_sqr(r, a); f12_mul(a3, r, a);
+    if (C_U_WNAF3[ZKV_U_WNAF3_LEN - 1] == 1) r = a; else r = a3;
     for (int i = ZKV_U_WNAF3_LEN - 2; i >= 0; i--) {
         ZKV_RENDEZVOUS();
-        f12_cyc_sqr(acc, acc);
+        f12_cyc_sqr(r, r);
         const int d = C_U_WNAF3[i];
-        if (d == 1 || d == -1) {
-            if ((d < 0) != neg1) { f12_conj(a1, a1); neg1 = !neg1; }
-            f12_mul(acc, acc, a1);
-        } else if (d) {
-            if ((d < 0) != neg3) { f12_conj(a3, a3); neg3 = !neg3; }
-            f12_mul(acc, acc, a3);
+        if (d) {
+            if (d < 0) f12_conj(r, r);
+            if (d == 1 || d == -1) f12_mul(r, r, a); else f12_mul(r, r, a3);
+            if (d < 0) f12_conj(r, r);
         }
     }
-    r = acc;
 }
-// GT = m^((p^6-1)(p^2+1)(L0 + L1 p + L2 p^2 + L3 p^3)), L_i as in DESIGN.md section 3 (same value as the oracle's final_exp)
+// GT = m^((p^6-1)(p^2+1)(L0 + L1 p + L2 p^2 + L3 p^3)), L_i as in DESIGN.md section 3 (same value as the oracle's final_exp).
+// Six Fp12 temporaries (the frame of this routine is the deepest of the path; every one of them is stack memory per thread).
 ZKV_HD ZKV_NOINLINE void final_exp(fp12& out, const fp12& m) {
-    fp12 f, t, t1;
+    fp12 f, t, t1, x, y, z;
     f12_conj(t, m); f12_inv(t1, m); f12_mul(f, t, t1);
-    f12_frob(t, f, 2); f12_mul(f, t, f);
-    fp12 fu, f2u, f6u, f6u2, a, b;
-    f12_pow_u(fu, f);
-    f12_cyc_sqr(f2u, fu); f12_cyc_sqr(t, f2u); f12_mul(f6u, t, f2u);
-    f12_pow_u(f6u2, f6u); f12_cyc_sqr(t, f6u2); f12_pow_u(t1, t);      // t1 = f^(12u^3)
-    f12_mul(a, t1, f6u2); f12_mul(a, a, f6u);
-    f12_conj(t, f2u); f12_mul(b, a, t);
-    f12_mul(t1, a, f6u2); f12_mul(t1, t1, f);
-    f12_frob(t, b, 1); f12_mul(t1, t1, t);
-    f12_frob(t, a, 2); f12_mul(t1, t1, t);
-    f12_conj(t, f); f12_mul(t, b, t); f12_frob(t, t, 3);
-    f12_mul(out, t1, t);
+    f12_frob(t, f, 2); f12_mul(f, t, f);                                   // f = m^((p^6-1)(p^2+1))
+    f12_pow_u(t, f);                                                       // t = f^u
+    f12_cyc_sqr(x, t); f12_cyc_sqr(t, x); f12_mul(y, t, x);                // x = f^(2u), y = f^(6u)
+    f12_pow_u(z, y); f12_cyc_sqr(t, z); f12_pow_u(t1, t);                  // z = f^(6u^2), t1 = f^(12u^3)
+    f12_mul(t, t1, z); f12_mul(t1, t, y);                                  // t1 = a = f^(12u^3 + 6u^2 + 6u)        (y is free now)
+    f12_conj(t, x); f12_mul(y, t1, t);                                     // y = b = a * f^(-2u)                   (x is free now)
+    f12_mul(t, t1, z); f12_mul(x, t, f);                                   // x = a * f^(6u^2) * f                  (z is free now)
+    f12_frob(t, y, 1); f12_mul(z, x, t);                                   // z = x * b^p
+    f12_frob(t, t1, 2); f12_mul(x, z, t);                                  // x = z * a^(p^2)
+    f12_conj(t, f); f12_mul(t1, y, t); f12_frob(t, t1, 3);                 // t = (b / f)^(p^3)
+    f12_mul(out, x, t);
 }
 
 // ------------------------------------------------------------------------------------------ G1: y^2 = x^3 + 3
