@@ -230,10 +230,10 @@ ZKV_HD ZKV_INLINE bool f12_is_one(const fp12& a) {
     for (int k = 1; k < 12; k++) for (int i = 0; i < 8; i++) t |= w[k].v[i];
     return t == 0;
 }
-ZKV_HD ZKV_NOINLINE void f12_mul(fp12& r, const fp12& a, const fp12& b) {
-    fp6 t0, t1, s0, s1, m;
-    f6_mul(t0, a.c0, b.c0); f6_mul(t1, a.c1, b.c1);
-    f6_add(s0, a.c0, a.c1); f6_add(s1, b.c0, b.c1); f6_mul(m, s0, s1);
+ZKV_HD ZKV_NOINLINE void f12_mul(fp12& r, const fp12& a, const fp12& b) {     // r may alias a or b
+    fp6 m, t0, t1;
+    f6_add(t0, a.c0, a.c1); f6_add(t1, b.c0, b.c1); f6_mul(m, t0, t1);
+    f6_mul(t0, a.c0, b.c0); f6_mul(t1, a.c1, b.c1);                        // a, b are dead from here on
     f6_sub(m, m, t0); f6_sub(r.c1, m, t1);
     f6_mul_v(t1, t1); f6_add(r.c0, t0, t1);
 }

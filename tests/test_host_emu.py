@@ -116,3 +116,19 @@ def test_g1_scalar_mul(emu):
     for k in (0, 1, 2, R - 1, R, R + 5, (1 << 256) - 1, rng.u256(), rng.u256()):
         emu.emu_g1_mul(G1, w32(k), out)
         assert out.raw == O.ec_mul(G1 + w32(k))
+
+
+def test_routines_with_large_temporaries_stay_out_of_line():
+    """Source rule from DESIGN.md section 5: nvcc's optimiser merged the stack slots of an INLINED routine's temporaries with live values
+    of the Miller loop.  The routines below hold Fp2-and-larger temporaries and are called from frames that keep values across the call,
+    so they must remain out of line; the Frobenius operands of the Miller loops must be computed inside the loop that uses them."""
+    src = open(os.path.join(ROOT, "stylus_zkvm_verifiers_b200", "csrc", "bn254.cuh")).read()
+    for name in ("f12_mul_line_at", "f12_mul_nline_at", "f12_mul_line", "f12_mul_line1", "miller_loop", "miller_loop_norm", "g2_precompute_lines",
+                 "g2_normalise_lines", "g1_slopes2", "line_dbl", "line_add", "f12_sqr", "f12_mul", "f6_mul", "f6_mul_01", "f12_pow_u", "final_exp"):
+        decl = [l for l in src.split("\n") if (" " + name + "(") in l and l.startswith("ZKV_HD")]
+        assert decl and all("ZKV_NOINLINE" in l for l in decl), name
+    for loop in ("miller_loop", "miller_loop_norm"):
+        body = src[src.index("void " + loop + "("):]
+        body = body[:body.index("\n}\n")]
+        tail = body[body.index("for (int s = 1; s <= 2; s++)"):]
+        assert "g2_frob_affine(xs, ys, s)" in tail and "fp2 x2" not in body, loop
