@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--n", type=int, default=1 << 16, help="proofs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exact-lines", action="store_true", help="verification path with the unscaled gamma / delta lines (A/B measurement)")
+    ap.add_argument("--segments", type=int, default=0, help="Miller loop segments per chunk (0 = library default)")
     ap.add_argument("--chunks", type=int, default=0, help="stream-overlap chunks per device batch (0 = library default)")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
@@ -230,6 +231,8 @@ def main():
 
     if args.exact_lines:
         Z.set_normalised_lines(0)
+    if args.segments:
+        Z.set_miller_segments(args.segments)
     if args.chunks:
         Z.set_overlap(args.chunks)
     chunks = Z.set_overlap(0)                    # 0 is out of range: reads the current value

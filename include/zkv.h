@@ -156,6 +156,10 @@ int zkv_set_overlap(int chunks);
  * coefficient is 1; the final exponentiation output and every status byte are unchanged).  On by default; 0 runs
  * the unscaled lines of the pairing service instead (A/B measurements, parity tests).  Returns the previous setting. */
 int zkv_set_normalised_lines(int on);
+/* Verification path: run the Miller loop of every chunk as `segments` kernels (f and R carried in HBM between them) so that the kernels of
+ * different chunks interleave at a finer grain than a whole loop (default 8; measured -2.6 % per step at 2^16 proofs).  Single-chain batches
+ * (under 8192 proofs, or zkv_set_overlap(1)) always use the one-kernel form.  Returns the previous value. */
+int zkv_set_miller_segments(int segments);
 /* integer-pipe microbenchmark (roofline denominator): returns measured IMAD.WIDE.U32 results/s and
  * Fp-multiplications/s on `device` */
 int zkv_imad_peak(int device, double* wide_per_s, double* fpmul_per_s);

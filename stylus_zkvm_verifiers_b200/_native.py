@@ -52,6 +52,7 @@ _SIGS = {
     "zkv_risc0_vk": (_P, [_P]),
     "zkv_sp1_vk": (_P, [_P]),
     "zkv_set_overlap": (C.c_int, [C.c_int]),
+    "zkv_set_miller_segments": (C.c_int, [C.c_int]),
     "zkv_set_normalised_lines": (C.c_int, [C.c_int]),
     "zkv_imad_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }

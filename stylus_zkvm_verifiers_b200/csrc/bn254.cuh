@@ -602,6 +602,37 @@ ZKV_HD ZKV_NOINLINE bool g2_normalise_lines(nline_t* out, const line_t* in, int 
 }
 // Verification-path Miller loop: pair 0 = (P0, variable Q), pairs 1, 2 = (P1, P2) against the normalised tables nt[0], nt[1].
 // xy[j] = xPj / yPj, iy[j] = 1 / yPj for the two fixed pairs (both zero for a pair that must contribute 1).
+// The loop can be run in SEGMENTS (digits d_hi down to d_lo of the NAF, the Frobenius lines with the last one): f and R are the state
+// carried between segments (the caller keeps them in HBM), so that the kernels of several chunks can interleave at a granularity finer
+// than one whole Miller loop.  miller_loop_norm is the single-segment form.
+ZKV_HD ZKV_NOINLINE void miller_loop_norm_seg(fp12& f, g2j& R, const fp& px0, const fp& py0, const fp2& qx, const fp2& qy,
+                                              const nline_t* const* nt, const fp* xy, const fp* iy, bool var_off, int d_hi, int d_lo, bool last) {
+    line_t l; int li = 0;
+    for (int d = ZKV_ATE_NAF_LEN - 2; d > d_hi; d--) li += 1 + (C_ATE_NAF[d] != 0);      // lines consumed by the earlier segments
+    for (int d = d_hi; d >= d_lo; d--) {
+        ZKV_RENDEZVOUS();
+        if (d != ZKV_ATE_NAF_LEN - 2) f12_sqr(f, f);
+        line_dbl(R, l); f12_mul_line_at(f, l, px0, py0, var_off);
+        for (int j = 0; j < 2; j++) f12_mul_nline_at(f, nt[j][li], xy[j], iy[j]);
+        li++;
+        int dg = C_ATE_NAF[d];
+        if (dg) {
+            fp2 y = qy; if (dg < 0) f2_neg(y, y);
+            line_add(R, qx, y, l); f12_mul_line_at(f, l, px0, py0, var_off);
+            for (int j = 0; j < 2; j++) f12_mul_nline_at(f, nt[j][li], xy[j], iy[j]);
+            li++;
+        }
+    }
+    if (!last) return;
+    for (int s = 1; s <= 2; s++) {
+        fp2 xs = qx, ys = qy; g2_frob_affine(xs, ys, s);
+        if (s == 2) f2_neg(ys, ys);
+        line_add(R, xs, ys, l); f12_mul_line_at(f, l, px0, py0, var_off);
+        for (int j = 0; j < 2; j++) f12_mul_nline_at(f, nt[j][li], xy[j], iy[j]);
+        li++;
+    }
+}
+// single-kernel form (own body: with compile-time loop bounds it is 3 % faster than the segment routine run over the whole range)
 ZKV_HD ZKV_NOINLINE void miller_loop_norm(fp12& f, const fp& px0, const fp& py0, const fp2& qx, const fp2& qy,
                                           const nline_t* const* nt, const fp* xy, const fp* iy, bool var_off) {
     f = f12_one();

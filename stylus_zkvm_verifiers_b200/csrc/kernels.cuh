@@ -231,6 +231,36 @@ __global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_miller_norm(int n, 
     if (i0 < n) out[i] = f;
 }
 
+// Segment form of k_miller_norm: digits d_hi .. d_lo of the loop; f (in `fio`) and R (in `rst`) are carried in HBM between segments, the
+// slopes of the two fixed pairs are computed by the first segment and kept in `sl` (4 Fp per proof).
+__global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_miller_norm_seg(int n, MillerArgs a, const uint8_t* flags, fp12* fio, g2j* rst, fp* sl,
+                                                                              int d_hi, int d_lo, int first, int last) {
+    int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = i0 < n ? i0 : n - 1;
+    uint8_t fl = flags[i];
+    uint32_t skip = a.vk_skip;
+    for (int j = 0; j < 3; j++) if (fl & a.skip_bit[j]) skip |= 1u << j;
+    if (fl & (F_INVALID | F_SELMIS)) skip = 0xF;
+    fp xy[2], iy[2];
+    if (first) {
+        fp x12[2] = {a.px[1][i], a.px[2][i]}, y12[2] = {a.py[1][i], a.py[2][i]};
+        bool off[2] = {(skip & 2u) != 0, (skip & 4u) != 0};
+        g1_slopes2(xy, iy, x12, y12, off);
+        if (i0 < n && !last) { sl[4 * (size_t)i] = xy[0]; sl[4 * (size_t)i + 1] = xy[1]; sl[4 * (size_t)i + 2] = iy[0]; sl[4 * (size_t)i + 3] = iy[1]; }
+    } else {
+        xy[0] = sl[4 * (size_t)i]; xy[1] = sl[4 * (size_t)i + 1]; iy[0] = sl[4 * (size_t)i + 2]; iy[1] = sl[4 * (size_t)i + 3];
+    }
+    fp px0 = a.px[0][i], py0 = a.py[0][i];
+    fp2 qx = a.qx[i], qy = a.qy[i];
+    fp12 f; g2j R;
+    if (first) { f = f12_one(); R.x = qx; R.y = qy; R.z = f2_one(); }
+    else { f = fio[i]; R = rst[i]; }
+    miller_loop_norm_seg(f, R, px0, py0, qx, qy, a.ntabs, xy, iy, (skip & 1u) != 0, d_hi, d_lo, last != 0);
+    if (last) { if (a.pre) { fp12 p = *a.pre; f12_mul(f, f, p); } }
+    else if (i0 < n) rst[i] = R;
+    if (i0 < n) fio[i] = f;
+}
+
 // K7 + K8: final exponentiation, is-one test and status byte
 __global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_final_exp(int n, const fp12* in, const uint8_t* flags, uint8_t* status, uint8_t* gt_out, int pairing_mode) {
     int i0 = blockIdx.x * blockDim.x + threadIdx.x;

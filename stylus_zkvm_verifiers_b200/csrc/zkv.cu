@@ -61,7 +61,7 @@ struct DevCtx {
     // workspace
     size_t cap = 0;
     fp* px[4] = {nullptr, nullptr, nullptr, nullptr}; fp* py[4] = {nullptr, nullptr, nullptr, nullptr};
-    fp2 *qx = nullptr, *qy = nullptr; fp12* f = nullptr; uint8_t *flags = nullptr, *status = nullptr; uint32_t* scal = nullptr; size_t scal_words = 0;
+    fp2 *qx = nullptr, *qy = nullptr; fp12* f = nullptr; g2j* rst = nullptr; fp* sl = nullptr; uint8_t *flags = nullptr, *status = nullptr; uint32_t* scal = nullptr; size_t scal_words = 0;
     // staging
     uint8_t* d_in = nullptr; size_t d_in_cap = 0; uint8_t* d_out = nullptr; size_t d_out_cap = 0;
     uint8_t* h_pin = nullptr; size_t h_pin_cap = 0; uint8_t* h_out = nullptr; size_t h_out_cap = 0;
@@ -78,10 +78,11 @@ struct DevCtx {
 static int ctx_reserve(DevCtx* c, size_t n, size_t scal_words_per_proof) {
     if (n > c->cap) {
         for (int j = 0; j < 4; j++) { cudaFree(c->px[j]); cudaFree(c->py[j]); }
-        cudaFree(c->qx); cudaFree(c->qy); cudaFree(c->f); cudaFree(c->flags); cudaFree(c->status);
+        cudaFree(c->qx); cudaFree(c->qy); cudaFree(c->f); cudaFree(c->flags); cudaFree(c->status); cudaFree(c->rst); cudaFree(c->sl);
         c->cap = 0;
         for (int j = 0; j < 4; j++) { CK(cudaMalloc(&c->px[j], n * sizeof(fp))); CK(cudaMalloc(&c->py[j], n * sizeof(fp))); }
         CK(cudaMalloc(&c->qx, n * sizeof(fp2))); CK(cudaMalloc(&c->qy, n * sizeof(fp2))); CK(cudaMalloc(&c->f, n * sizeof(fp12)));
+        CK(cudaMalloc(&c->rst, n * sizeof(g2j))); CK(cudaMalloc(&c->sl, n * 4 * sizeof(fp)));
         CK(cudaMalloc(&c->flags, n)); CK(cudaMalloc(&c->status, n));
         c->cap = n;
     }
@@ -100,7 +101,7 @@ static void ctx_free(DevCtx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     for (int j = 0; j < 4; j++) { cudaFree(c->px[j]); cudaFree(c->py[j]); }
-    cudaFree(c->qx); cudaFree(c->qy); cudaFree(c->f); cudaFree(c->flags); cudaFree(c->status); cudaFree(c->scal);
+    cudaFree(c->qx); cudaFree(c->qy); cudaFree(c->f); cudaFree(c->flags); cudaFree(c->status); cudaFree(c->scal); cudaFree(c->rst); cudaFree(c->sl);
     cudaFree(c->d_in); cudaFree(c->d_out); cudaFreeHost(c->h_pin); cudaFreeHost(c->h_out);
     cudaFree(c->d_vk); cudaFree(c->d_lines); cudaFree(c->d_nlines); cudaFree(c->d_pre); cudaFree(c->d_tab); cudaFree(c->d_ic0);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -209,6 +210,8 @@ __global__ void k_status_all_fail(int n, const uint8_t* flags, uint8_t* status) 
 // with per-stage events (what bench.py uses for the per-kernel roofline figures).
 static int g_normalised_lines = 1;      // verification path: gamma / delta lines scaled to (1, n3, n4): 10 instead of 13 Fp2 multiplications per line
 extern "C" int zkv_set_normalised_lines(int on) { int old = g_normalised_lines; if (on == 0 || on == 1) g_normalised_lines = on; return old; }
+static int g_miller_segments = 8;       // > 1: the verification Miller loop runs as that many segment kernels per chunk (state in HBM between them)
+extern "C" int zkv_set_miller_segments(int s) { int old = g_miller_segments; if (s >= 1 && s <= 16) g_miller_segments = s; return old; }
 static int g_overlap_chunks = 2;
 extern "C" int zkv_set_overlap(int chunks) { int old = g_overlap_chunks; if (chunks >= 1 && chunks <= 64) g_overlap_chunks = chunks; return old; }
 
@@ -249,7 +252,13 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
     const bool norm = c->h_vk.norm_ok && g_normalised_lines;
     a.skip_bit[0] = F_SKIP0; a.skip_bit[1] = F_SKIPX; a.skip_bit[2] = F_SKIPC;
     a.vk_skip = (uint8_t)((c->h_vk.g2_inf[1] ? 2 : 0) | (c->h_vk.g2_inf[2] ? 4 : 0));
-    if (norm) k_miller_norm<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, a, flags, c->f + o);
+    if (norm && g_miller_segments > 1 && !timed) {      // a timed single chain (per-stage roofline pass, small batches) runs the one-kernel form
+        const int S = g_miller_segments, top = ZKV_ATE_NAF_LEN - 2;           // digits top .. 0 in S nearly equal runs
+        for (int k = 0; k < S; k++) {
+            int hi = top - (top + 1) * k / S, lo = top - (top + 1) * (k + 1) / S + 1;
+            k_miller_norm_seg<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, a, flags, c->f + o, c->rst + o, c->sl + 4 * o, hi, lo, k == 0, k == S - 1);
+        }
+    } else if (norm) k_miller_norm<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, a, flags, c->f + o);
     else k_miller<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, a, flags, c->f + o);
     if (timed) CK(cudaEventRecord(c->ev[4], s));
     k_final_exp<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, c->f + o, flags, j.d_status + jo, nullptr, 0);

@@ -301,6 +301,11 @@ def set_overlap(chunks):
     return N.lib().zkv_set_overlap(int(chunks))
 
 
+def set_miller_segments(segments):
+    """Verification path: Miller loop as `segments` kernels per chunk (1 = one kernel); returns the previous value."""
+    return N.lib().zkv_set_miller_segments(int(segments))
+
+
 def set_normalised_lines(on):
     """Verification path: normalised gamma / delta line tables on (default) or off; returns the previous setting."""
     return N.lib().zkv_set_normalised_lines(int(on))

@@ -426,3 +426,27 @@ def test_scale_sp1_mixed_and_pairing(Z, gpu, fx):
     blob = b"".join(g1s[i][0:64] + g2s[i] + g1s[i][64:128] + vk0.beta + g1s[i][128:192] + vk0.gamma + g1s[i][192:256] + vk0.delta for i in range(sub))
     ook, ogt, oml = O.pairing4_batch(blob, sub, want_gt=True, want_miller=True)
     assert ok[:sub].tolist() == list(ook) and bytes(gt[:384 * sub]) == bytes(ogt) and bytes(ml[:384 * sub]) == bytes(oml)
+
+
+def test_segmented_miller_loop_matches(Z, gpu, fx):
+    """The verification Miller loop run as 2, 4 and 7 segment kernels (state carried in HBM) gives the same status bytes as the single
+    kernel and as the oracle, on a mixed batch large enough to be cut into stream chunks."""
+    from stylus_zkvm_verifiers_b200 import synth as S
+    vk = S.make_vk(gpu, 0, 6, 0xB200000B)
+    kv = Z.VerificationKey(0, vk.alpha, vk.beta, vk.gamma, vk.delta, vk.ic)
+    v = Z.RiscZeroVerifier(kv); v.initialize(fx["control_root"], fx["bn254_control_id"])
+    n = 9000
+    batch = S.make_risc0_batch(gpu, vk, v.get_selector(), fx["control_root"], fx["bn254_control_id"], fx["sys0"], n, 0xB200000B, pool=64)
+    S.mutate_risc0(batch, gpu, S.SplitMix64(0xB200000C))
+    ro = O.Risc0Oracle(oracle_vk(vk)); ro.initialize(fx["control_root"], fx["bn254_control_id"])
+    sub = 600
+    want = ro.verify_batch(batch.seals[:sub], batch.image_ids[:sub], batch.journals[:sub])
+    prev = Z.set_miller_segments(1)
+    try:
+        base = v.verify_batch(batch.seals, batch.image_ids, batch.journals)
+        assert base[:sub].tolist() == want.tolist()
+        for segs in (2, 4, 7):
+            Z.set_miller_segments(segs)
+            assert v.verify_batch(batch.seals, batch.image_ids, batch.journals).tolist() == base.tolist(), segs
+    finally:
+        Z.set_miller_segments(prev)

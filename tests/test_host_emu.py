@@ -123,11 +123,11 @@ def test_routines_with_large_temporaries_stay_out_of_line():
     of the Miller loop.  The routines below hold Fp2-and-larger temporaries and are called from frames that keep values across the call,
     so they must remain out of line; the Frobenius operands of the Miller loops must be computed inside the loop that uses them."""
     src = open(os.path.join(ROOT, "stylus_zkvm_verifiers_b200", "csrc", "bn254.cuh")).read()
-    for name in ("f12_mul_line_at", "f12_mul_nline_at", "f12_mul_line", "f12_mul_line1", "miller_loop", "miller_loop_norm", "g2_precompute_lines",
+    for name in ("f12_mul_line_at", "f12_mul_nline_at", "f12_mul_line", "f12_mul_line1", "miller_loop", "miller_loop_norm", "miller_loop_norm_seg", "g2_precompute_lines",
                  "g2_normalise_lines", "g1_slopes2", "line_dbl", "line_add", "f12_sqr", "f12_mul", "f6_mul", "f6_mul_01", "f12_pow_u", "final_exp"):
         decl = [l for l in src.split("\n") if (" " + name + "(") in l and l.startswith("ZKV_HD")]
         assert decl and all("ZKV_NOINLINE" in l for l in decl), name
-    for loop in ("miller_loop", "miller_loop_norm"):
+    for loop in ("miller_loop", "miller_loop_norm", "miller_loop_norm_seg"):
         body = src[src.index("void " + loop + "("):]
         body = body[:body.index("\n}\n")]
         tail = body[body.index("for (int s = 1; s <= 2; s++)"):]
