@@ -160,6 +160,12 @@ int zkv_set_normalised_lines(int on);
  * different chunks interleave at a finer grain than a whole loop (default 8; measured -2.6 % per step at 2^16 proofs).  Single-chain batches
  * (under 8192 proofs, or zkv_set_overlap(1)) always use the one-kernel form.  Returns the previous value. */
 int zkv_set_miller_segments(int segments);
+/* Verification path: chunked batches of at most 2^18 proofs run the final exponentiation as four stage kernels with their state (five
+ * Fp12 per proof) in HBM, for the same reason as zkv_set_miller_segments.  On by default; returns the previous setting. */
+int zkv_set_final_exp_stages(int on);
+/* Kernels launched by the verification chains (decode .. final exponentiation, every chunk, segment and stage) since the library was
+ * loaded; bench.py reports the difference over its timed region as gpu_launches. */
+unsigned long long zkv_launch_count(void);
 /* integer-pipe microbenchmark (roofline denominator): returns measured IMAD.WIDE.U32 results/s and
  * Fp-multiplications/s on `device` */
 int zkv_imad_peak(int device, double* wide_per_s, double* fpmul_per_s);

@@ -52,8 +52,10 @@ _SIGS = {
     "zkv_risc0_vk": (_P, [_P]),
     "zkv_sp1_vk": (_P, [_P]),
     "zkv_set_overlap": (C.c_int, [C.c_int]),
+    "zkv_set_final_exp_stages": (C.c_int, [C.c_int]),
     "zkv_set_miller_segments": (C.c_int, [C.c_int]),
     "zkv_set_normalised_lines": (C.c_int, [C.c_int]),
+    "zkv_launch_count": (C.c_ulonglong, []),
     "zkv_imad_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 EXPORTS = tuple(_SIGS)

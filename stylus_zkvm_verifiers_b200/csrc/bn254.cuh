@@ -337,6 +337,35 @@ ZKV_HD ZKV_NOINLINE void final_exp(fp12& out, const fp12& m) {
     f12_mul(out, x, t);
 }
 
+// final_exp in four stages for the segmented kernels (same operations in the same order; the values named in final_exp are the state):
+//   stage 0: m -> f, t = f^u          stage 1: t -> x = f^(2u), y = f^(6u), z = f^(6u^2)
+//   stage 2: z -> t1 = f^(12u^3)      stage 3: f, x, y, z, t1 -> result
+ZKV_HD ZKV_NOINLINE void final_exp_stage0(fp12& f, fp12& t, const fp12& m) {
+    fp12 t1;
+    f12_conj(t, m); f12_inv(t1, m); f12_mul(f, t, t1);
+    f12_frob(t, f, 2); f12_mul(f, t, f);
+    f12_pow_u(t, f);
+}
+ZKV_HD ZKV_NOINLINE void final_exp_stage1(fp12& x, fp12& y, fp12& z, const fp12& tin) {
+    fp12 t;
+    f12_cyc_sqr(x, tin); f12_cyc_sqr(t, x); f12_mul(y, t, x);
+    f12_pow_u(z, y);
+}
+ZKV_HD ZKV_NOINLINE void final_exp_stage2(fp12& t1, const fp12& z) {
+    fp12 t;
+    f12_cyc_sqr(t, z); f12_pow_u(t1, t);
+}
+ZKV_HD ZKV_NOINLINE void final_exp_stage3(fp12& out, const fp12& f, fp12& x, fp12& y, fp12& z, fp12& t1) {   // x, y, z, t1 are consumed
+    fp12 t;
+    f12_mul(t, t1, z); f12_mul(t1, t, y);
+    f12_conj(t, x); f12_mul(y, t1, t);
+    f12_mul(t, t1, z); f12_mul(x, t, f);
+    f12_frob(t, y, 1); f12_mul(z, x, t);
+    f12_frob(t, t1, 2); f12_mul(x, z, t);
+    f12_conj(t, f); f12_mul(t1, y, t); f12_frob(t, t1, 3);
+    f12_mul(out, x, t);
+}
+
 // ------------------------------------------------------------------------------------------ G1: y^2 = x^3 + 3
 struct g1j { fp x, y, z; };            // Jacobian; z == 0 is infinity
 ZKV_HD ZKV_INLINE bool g1_on_curve(const fp& x, const fp& y) {

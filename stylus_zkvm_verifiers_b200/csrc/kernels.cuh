@@ -278,6 +278,34 @@ __global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_final_exp(int n, co
     status[i] = pairing_mode ? (one ? 1 : 0) : (one ? ST_OK : ST_VERIFICATION_FAILED);
     if (gt_out) f12_to_bytes(gt_out + (size_t)i * 384, gt);
 }
+// Staged form of k_final_exp (bn254.cuh final_exp_stage0..3): the state (f, x, y, z, t1; slot 1 first holds t = f^u) lives in `st`, five
+// Fp12 per proof, so that the three exponentiations by u of different chunks can interleave.  Stage 3 writes the status like k_final_exp.
+__global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_final_exp_stage(int n, int stage, const fp12* in, fp12* st, const uint8_t* flags, uint8_t* status) {
+    int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = i0 < n ? i0 : n - 1;
+    const bool w = i0 < n;
+    fp12* s = st + 5 * (size_t)i;
+    if (stage == 0) {
+        fp12 m = in[i], f, t;
+        final_exp_stage0(f, t, m);
+        if (w) { s[0] = f; s[1] = t; }
+    } else if (stage == 1) {
+        fp12 t = s[1], x, y, z;
+        final_exp_stage1(x, y, z, t);
+        if (w) { s[1] = x; s[2] = y; s[3] = z; }
+    } else if (stage == 2) {
+        fp12 z = s[3], t1;
+        final_exp_stage2(t1, z);
+        if (w) s[4] = t1;
+    } else {
+        fp12 f = s[0], x = s[1], y = s[2], z = s[3], t1 = s[4], gt;
+        final_exp_stage3(gt, f, x, y, z, t1);
+        if (!w) return;
+        uint8_t fl = flags[i];
+        if (fl & (F_INVALID | F_SELMIS)) { status[i] = (fl & F_SELMIS) ? ST_SELECTOR_MISMATCH : ST_VERIFICATION_FAILED; return; }
+        status[i] = f12_is_one(gt) ? ST_OK : ST_VERIFICATION_FAILED;
+    }
+}
 // parity hook: one Fp12 tower operation per thread on byte operands (12 x BE-32 each, tower order).
 // op 0: a*b  1: a^2  2: a * line(b.c0.c0, b.c0.c1, b.c0.c2)  3: cyclotomic square  4: 1/a  5..7: Frobenius^(op-4)  8: final exponentiation  9: single-pair Miller loop
 __global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_fp12_op(int n, int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {

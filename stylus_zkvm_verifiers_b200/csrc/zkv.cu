@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -61,7 +62,7 @@ struct DevCtx {
     // workspace
     size_t cap = 0;
     fp* px[4] = {nullptr, nullptr, nullptr, nullptr}; fp* py[4] = {nullptr, nullptr, nullptr, nullptr};
-    fp2 *qx = nullptr, *qy = nullptr; fp12* f = nullptr; g2j* rst = nullptr; fp* sl = nullptr; uint8_t *flags = nullptr, *status = nullptr; uint32_t* scal = nullptr; size_t scal_words = 0;
+    fp2 *qx = nullptr, *qy = nullptr; fp12* f = nullptr; g2j* rst = nullptr; fp* sl = nullptr; fp12* fes = nullptr; size_t fes_cap = 0; uint8_t *flags = nullptr, *status = nullptr; uint32_t* scal = nullptr; size_t scal_words = 0;
     // staging
     uint8_t* d_in = nullptr; size_t d_in_cap = 0; uint8_t* d_out = nullptr; size_t d_out_cap = 0;
     uint8_t* h_pin = nullptr; size_t h_pin_cap = 0; uint8_t* h_out = nullptr; size_t h_out_cap = 0;
@@ -75,6 +76,8 @@ struct DevCtx {
     std::mutex mu;
 };
 
+static int g_final_exp_stages = 1;      // 1: chunked batches run the final exponentiation as four stage kernels (state: 5 Fp12 per proof in HBM)
+extern "C" int zkv_set_final_exp_stages(int on) { int old = g_final_exp_stages; if (on == 0 || on == 1) g_final_exp_stages = on; return old; }
 static int ctx_reserve(DevCtx* c, size_t n, size_t scal_words_per_proof) {
     if (n > c->cap) {
         for (int j = 0; j < 4; j++) { cudaFree(c->px[j]); cudaFree(c->py[j]); }
@@ -85,6 +88,10 @@ static int ctx_reserve(DevCtx* c, size_t n, size_t scal_words_per_proof) {
         CK(cudaMalloc(&c->rst, n * sizeof(g2j))); CK(cudaMalloc(&c->sl, n * 4 * sizeof(fp)));
         CK(cudaMalloc(&c->flags, n)); CK(cudaMalloc(&c->status, n));
         c->cap = n;
+    }
+    if (g_final_exp_stages && n >= 8192 && n <= ((size_t)1 << 18) && n > c->fes_cap) {      // staged final exponentiation: 1.9 KB per proof, bounded to 2^18 proofs (0.5 GB)
+        cudaFree(c->fes); c->fes = nullptr; c->fes_cap = 0;
+        CK(cudaMalloc(&c->fes, n * 5 * sizeof(fp12))); c->fes_cap = n;
     }
     size_t need = n * scal_words_per_proof;
     if (need > c->scal_words) { cudaFree(c->scal); c->scal_words = 0; CK(cudaMalloc(&c->scal, need * 4)); c->scal_words = need; }
@@ -101,7 +108,7 @@ static void ctx_free(DevCtx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     for (int j = 0; j < 4; j++) { cudaFree(c->px[j]); cudaFree(c->py[j]); }
-    cudaFree(c->qx); cudaFree(c->qy); cudaFree(c->f); cudaFree(c->flags); cudaFree(c->status); cudaFree(c->scal); cudaFree(c->rst); cudaFree(c->sl);
+    cudaFree(c->qx); cudaFree(c->qy); cudaFree(c->f); cudaFree(c->flags); cudaFree(c->status); cudaFree(c->scal); cudaFree(c->rst); cudaFree(c->sl); cudaFree(c->fes);
     cudaFree(c->d_in); cudaFree(c->d_out); cudaFreeHost(c->h_pin); cudaFreeHost(c->h_out);
     cudaFree(c->d_vk); cudaFree(c->d_lines); cudaFree(c->d_nlines); cudaFree(c->d_pre); cudaFree(c->d_tab); cudaFree(c->d_ic0);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -213,6 +220,8 @@ extern "C" int zkv_set_normalised_lines(int on) { int old = g_normalised_lines; 
 static int g_miller_segments = 8;       // > 1: the verification Miller loop runs as that many segment kernels per chunk (state in HBM between them)
 extern "C" int zkv_set_miller_segments(int s) { int old = g_miller_segments; if (s >= 1 && s <= 16) g_miller_segments = s; return old; }
 static int g_overlap_chunks = 2;
+static std::atomic<unsigned long long> g_launches{0};   // kernels launched by the verification chains since load (bench.py's gpu_launches)
+extern "C" unsigned long long zkv_launch_count(void) { return g_launches.load(); }
 extern "C" int zkv_set_overlap(int chunks) { int old = g_overlap_chunks; if (chunks >= 1 && chunks <= 64) g_overlap_chunks = chunks; return old; }
 
 // the kernel chain for proofs [o, o+m) of job j on stream s; stage events only when `timed`
@@ -235,6 +244,7 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
     if (timed) CK(cudaEventRecord(c->ev[1], s));
     if (j.all_fail || !vk->valid) {
         k_status_all_fail<<<nblk(m), TPB, 0, s>>>(m, flags, j.d_status + jo);
+        g_launches += 3;
         if (timed) for (int e = 2; e < 6; e++) CK(cudaEventRecord(c->ev[e], s));
         CK(cudaGetLastError());
         return 0;
@@ -250,6 +260,7 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
     a.nfixed = 2; a.pre = c->d_pre;
     a.ntabs[0] = c->d_nlines; a.ntabs[1] = c->d_nlines + ZKV_LINES_PER_G2;
     const bool norm = c->h_vk.norm_ok && g_normalised_lines;
+    int nl = 4;                             // decode, signals, vk_x, G2 check
     a.skip_bit[0] = F_SKIP0; a.skip_bit[1] = F_SKIPX; a.skip_bit[2] = F_SKIPC;
     a.vk_skip = (uint8_t)((c->h_vk.g2_inf[1] ? 2 : 0) | (c->h_vk.g2_inf[2] ? 4 : 0));
     if (norm && g_miller_segments > 1 && !timed) {      // a timed single chain (per-stage roofline pass, small batches) runs the one-kernel form
@@ -258,11 +269,16 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
             int hi = top - (top + 1) * k / S, lo = top - (top + 1) * (k + 1) / S + 1;
             k_miller_norm_seg<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, a, flags, c->f + o, c->rst + o, c->sl + 4 * o, hi, lo, k == 0, k == S - 1);
         }
+        nl += S - 1;
     } else if (norm) k_miller_norm<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, a, flags, c->f + o);
     else k_miller<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, a, flags, c->f + o);
     if (timed) CK(cudaEventRecord(c->ev[4], s));
-    k_final_exp<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, c->f + o, flags, j.d_status + jo, nullptr, 0);
+    if (g_final_exp_stages && !timed && c->fes && c->fes_cap >= o + (size_t)m) {
+        for (int st = 0; st < 4; st++) k_final_exp_stage<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, st, c->f + o, c->fes + 5 * o, flags, j.d_status + jo);
+        nl += 3;
+    } else k_final_exp<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, c->f + o, flags, j.d_status + jo, nullptr, 0);
     if (timed) CK(cudaEventRecord(c->ev[5], s));
+    g_launches += nl + 2;                   // + Miller loop (first or only kernel) + final exponentiation (first or only kernel)
     CK(cudaGetLastError());
     return 0;
 }

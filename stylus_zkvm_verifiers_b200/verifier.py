@@ -301,6 +301,16 @@ def set_overlap(chunks):
     return N.lib().zkv_set_overlap(int(chunks))
 
 
+def launch_count():
+    """Kernels launched by the verification chains since the library was loaded."""
+    return int(N.lib().zkv_launch_count())
+
+
+def set_final_exp_stages(on):
+    """Verification path: staged final exponentiation for chunked batches on (default) or off; returns the previous setting."""
+    return N.lib().zkv_set_final_exp_stages(int(on))
+
+
 def set_miller_segments(segments):
     """Verification path: Miller loop as `segments` kernels per chunk (1 = one kernel); returns the previous value."""
     return N.lib().zkv_set_miller_segments(int(segments))

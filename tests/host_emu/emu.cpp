@@ -16,6 +16,11 @@ int emu_f12_sqr(const uint8_t* a, uint8_t* out) { fp12 x, z; dec_f12(x, a); f12_
 int emu_f12_cyc_sqr(const uint8_t* a, uint8_t* out) { fp12 x, z; dec_f12(x, a); f12_cyc_sqr(z, x); f12_to_bytes(out, z); return 0; }
 int emu_f12_inv(const uint8_t* a, uint8_t* out) { fp12 x, z; dec_f12(x, a); f12_inv(z, x); f12_to_bytes(out, z); return 0; }
 int emu_final_exp(const uint8_t* a, uint8_t* out) { fp12 x, z; dec_f12(x, a); final_exp(z, x); f12_to_bytes(out, z); return 0; }
+int emu_final_exp_staged(const uint8_t* a, uint8_t* out) {
+    fp12 m, f, x, y, z, t1, r; dec_f12(m, a);
+    final_exp_stage0(f, x, m); { fp12 t = x; final_exp_stage1(x, y, z, t); } final_exp_stage2(t1, z); final_exp_stage3(r, f, x, y, z, t1);
+    f12_to_bytes(out, r); return 0;
+}
 // 1 = in G2, 0 = on twist but not in G2, 2 = not on twist / bad encoding
 int emu_g2_check(const uint8_t* q) { fp2 x, y; if (!dec_g2(x, y, q)) return 2; if (!g2_on_curve(x, y)) return 2; return g2_in_subgroup(x, y) ? 1 : 0; }
 // 4-pair Miller loop + final exp the way k_miller does it: pair 0 variable G2, pairs 1..3 from line tables of the three fixed points

@@ -448,5 +448,11 @@ def test_segmented_miller_loop_matches(Z, gpu, fx):
         for segs in (2, 4, 7):
             Z.set_miller_segments(segs)
             assert v.verify_batch(batch.seals, batch.image_ids, batch.journals).tolist() == base.tolist(), segs
+        for fe in (0, 1):                                  # one-kernel / staged final exponentiation
+            prev_fe = Z.set_final_exp_stages(fe)
+            try:
+                assert v.verify_batch(batch.seals, batch.image_ids, batch.journals).tolist() == base.tolist(), ("fe", fe)
+            finally:
+                Z.set_final_exp_stages(prev_fe)
     finally:
         Z.set_miller_segments(prev)

@@ -71,6 +71,15 @@ def test_final_exp_and_cyclotomic(emu):
         assert out.raw == O.fp12_mul(gt, gt) == O.fp12_cyc_sqr(gt)
 
 
+def test_staged_final_exp_equals_single(emu):
+    rng = SplitMix64(21)
+    a, b = C.create_string_buffer(384), C.create_string_buffer(384)
+    for _ in range(3):
+        x = rand_f12(rng)
+        emu.emu_final_exp(x, a); emu.emu_final_exp_staged(x, b)
+        assert a.raw == b.raw == O.final_exp(x)
+
+
 def test_g2_subgroup_test_matches_oracle(emu):
     rng = SplitMix64(13)
     for k in (1, 2, 3, R - 1, rng.fr(), rng.fr()):
