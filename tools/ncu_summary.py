@@ -56,8 +56,10 @@ def main(out, reps):
             if name in ("k_miller", "k_miller_norm", "k_final_exp") and d["proofs"] >= 1024:
                 d["source_page"] = source_mix(rep, name)
             kernels.append(d)
-    json.dump({"source": "ncu --set full --import-source on --clock-control none ... python bench.py --steps 1 --warmup 3 --no-cpu-baseline --chunks 1 (2^16 RISC Zero-shape proofs, "
-                         "one serial kernel chain); the .ncu-rep files stay in gpurun_out/ (60 MB each)",
+    json.dump({"source": "ncu --set full --import-source on --clock-control none ... python bench.py --steps 1 --warmup 3 --no-cpu-baseline [--chunks 1] (2^16 RISC Zero-shape proofs): "
+                         "the one-kernel forms (k_vkx, k_g2_check, k_miller_norm, k_final_exp) come from the serial single-chain pass (--chunks 1, report *_serial), the segment / stage kernels "
+                         "(k_miller_norm_seg, k_final_exp_stage: one chunk of 2^15 proofs, in launch order) from the default chunked path (report *_chunked); tools/profile_r1.sh is the recipe; "
+                         "the .ncu-rep files (60 MB each) are not kept",
                "note": "per-launch times under ncu are serialised and cold-cache: bench.py's live CUDA-event timings are the reported figures.  IMAD.WIDE issues once per 4 cycles "
                        "per scheduler, so a 25 % issue share of IMAD.WIDE would be 100 % of the integer-multiply roofline.",
                "kernels": kernels}, open(out, "w"), indent=1)
