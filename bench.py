@@ -202,7 +202,7 @@ def main():
     t8 = lambda blobs: torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8).cuda()
     if args.shape == "risc0":
         d_a, d_b, d_c = t8(batch.seals), t8(batch.image_ids), t8(batch.journals)
-        launch = lambda st, stream: v.verify_batch_device(dev, d_a.data_ptr(), d_b.data_ptr(), d_c.data_ptr(), n, st.data_ptr(), stream)
+        launch = lambda st, stream, m=n: v.verify_batch_device(dev, d_a.data_ptr(), d_b.data_ptr(), d_c.data_ptr(), m, st.data_ptr(), stream)
         h_blob = np.frombuffer(b"".join(batch.seals), dtype=np.uint8); h_off = np.arange(n + 1, dtype=np.uint64) * 260
         h_b = np.frombuffer(b"".join(batch.image_ids), dtype=np.uint8); h_c = np.frombuffer(b"".join(batch.journals), dtype=np.uint8)
         e2e_call = lambda out: v.verify_batch_packed(h_blob, h_off, h_b, h_c, n, out)
@@ -210,7 +210,7 @@ def main():
         W_M = W_RISC0_M
     else:
         d_a, d_b, d_c = t8(batch.proofs), t8(batch.vkeys), t8(batch.public_values)
-        launch = lambda st, stream: v.verify_batch_device(dev, d_b.data_ptr(), d_c.data_ptr(), 96, d_a.data_ptr(), n, st.data_ptr(), stream)
+        launch = lambda st, stream, m=n: v.verify_batch_device(dev, d_b.data_ptr(), d_c.data_ptr(), 96, d_a.data_ptr(), m, st.data_ptr(), stream)
         h_blob = np.frombuffer(b"".join(batch.proofs), dtype=np.uint8); h_off = np.arange(n + 1, dtype=np.uint64) * 260
         h_b = np.frombuffer(b"".join(batch.vkeys), dtype=np.uint8); h_c = np.frombuffer(b"".join(batch.public_values), dtype=np.uint8)
         h_voff = np.arange(n + 1, dtype=np.uint64) * 96
@@ -254,6 +254,20 @@ def main():
         launch(d_st, sp); torch.cuda.synchronize()
         for name, ms in v.stage_ms(dev).items():
             stage_sum[name] = stage_sum.get(name, 0.0) + ms / stage_reps
+    # roofline launches: a whole number of waves of the kernel in question (prefix of the same batch), so that the figure is the kernel's
+    # rate and not the batch's tail: a serial chain over all n proofs pays for a full last wave whatever its fill
+    def whole_waves(kernel):
+        w = Z.wave_proofs(dev, kernel)
+        return (n // w) * w if n >= w else n
+    wave_ms, wave_n = {}, {}
+    for name, kernel in (("miller", 0), ("final_exp", 1)):
+        m = whole_waves(kernel); wave_n[name] = m; acc = 0.0
+        launch(d_st, sp, m); torch.cuda.synchronize()
+        for k in range(stage_reps):
+            flush_ = torch.empty(256 << 20, dtype=torch.uint8, device="cuda").fill_(k); del flush_
+            launch(d_st, sp, m); torch.cuda.synchronize()
+            acc += v.stage_ms(dev)[name] / stage_reps
+        wave_ms[name] = acc
     Z.set_overlap(chunks)
     launch(d_st, sp); torch.cuda.synchronize()
 
@@ -290,9 +304,10 @@ def main():
     dev_ms, e2e_s = float(t[0].item()), float(t[1].item())
     total = n * world * args.steps
     value = total / (dev_ms * 1e-3)
-    miller_ms = stage_sum.get("miller", 0.0)
-    fe_ms = stage_sum.get("final_exp", 0.0)
-    mac_miller = n * W_MILLER3_M * M_MAC32
+    miller_ms, miller_n = wave_ms["miller"], wave_n["miller"]
+    fe_ms, fe_n = wave_ms["final_exp"], wave_n["final_exp"]
+    mac_miller = miller_n * W_MILLER3_M * M_MAC32
+    serial_miller_ms = stage_sum.get("miller", 0.0)
     miller_kernel = "k_miller" if args.exact_lines else "k_miller_norm"    # verification path: normalised gamma / delta lines by default
     line = {
         "metric": "groth16_verifies_per_sec", "value": value, "unit": "verifies/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -301,7 +316,7 @@ def main():
         "config": {"workload": "configs[1]: 2^%d synthetic %s-shape Groth16 proofs per GPU per step (%d public inputs, fixed random vk, trapdoor-simulated, all valid)" %
                    (n.bit_length() - 1, "RISC Zero" if args.shape == "risc0" else "SP1 v5", 5 if args.shape == "risc0" else 2),
                    "proofs_per_gpu": n, "l2": "flushed between timed steps (256 MiB fill)", "sharding": "contiguous proof ranges, no collective",
-                   "overlap": "%d chunks per device batch on side streams (stage_ms / roofline are from a serial single-chain pass)" % chunks},
+                   "overlap": "%d chunks per device batch on side streams (stage_ms: serial single-chain pass over all proofs; roofline: serial single-chain launches of a whole number of waves)" % chunks},
         "e2e": {"value": total / e2e_s, "unit": "verifies/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": n},
         "gpu_launches": launches,
         "stage_ms": stage_sum,
@@ -310,7 +325,10 @@ def main():
                      "peak_source": "IMAD.WIDE.U32 issue rate measured live on this GPU (zkv_imad_peak); MEASURED_PEAKS.json holds no integer figure",
                      "fpmul_chain_per_s": fpmul_peak,
                      "whole_path_frac": value / world * W_M * M_MAC32 / imad_peak,
-                     "final_exp_frac": (n * W_FINALEXP_M * M_MAC32 / (fe_ms * 1e-3)) / imad_peak if fe_ms else None},
+                     "final_exp_frac": (fe_n * W_FINALEXP_M * M_MAC32 / (fe_ms * 1e-3)) / imad_peak if fe_ms else None,
+                     "launch": {"proofs": miller_n, "ms": miller_ms, "note": "one k_miller_norm launch over a whole number of its waves (prefix of the batch), serial chain, CUDA events on the launching stream"},
+                     "final_exp_launch": {"proofs": fe_n, "ms": fe_ms},
+                     "frac_serial_all_proofs": (n * W_MILLER3_M * M_MAC32 / (serial_miller_ms * 1e-3)) / imad_peak if serial_miller_ms else None},
         "clocks": clocks.summary(),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

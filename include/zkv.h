@@ -149,7 +149,7 @@ int zkv_g2_check_batch(const uint8_t* g2s, size_t n, uint8_t* out, int device);
  * [0] decode+hash [1] vk_x [2] g2 check [3] miller [4] final exp ; returns number of entries */
 int zkv_last_stage_ms(const void* handle_vk, int device, float* out, int cap);
 /* A device batch is cut into `chunks` pieces whose kernel chains run on side streams of the device context, so the partial last wave of
- * one kernel is back-filled by blocks of another (default 2; batches under 8192 proofs are never cut).  chunks = 1 runs one chain on the
+ * one kernel is back-filled by blocks of another (default 4; batches under 8192 proofs are never cut).  chunks = 1 runs one chain on the
  * main stream and records the per-stage events zkv_last_stage_ms reads.  Process-wide; returns the previous value. */
 int zkv_set_overlap(int chunks);
 /* Verification path only: use the per-key normalised gamma / delta line tables (lines scaled by a subfield element so that their first
@@ -166,6 +166,9 @@ int zkv_set_final_exp_stages(int on);
 /* Kernels launched by the verification chains (decode .. final exponentiation, every chunk, segment and stage) since the library was
  * loaded; bench.py reports the difference over its timed region as gpu_launches. */
 unsigned long long zkv_launch_count(void);
+/* Proofs in one full wave of a heavy kernel on `device` (SM count x resident blocks per SM x 128 threads): kernel 0 = the verification
+ * Miller loop, 1 = the final exponentiation.  bench.py times whole-wave launches for its roofline figures.  Negative = error. */
+long long zkv_wave_proofs(int device, int kernel);
 /* integer-pipe microbenchmark (roofline denominator): returns measured IMAD.WIDE.U32 results/s and
  * Fp-multiplications/s on `device` */
 int zkv_imad_peak(int device, double* wide_per_s, double* fpmul_per_s);

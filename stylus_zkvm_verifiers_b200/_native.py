@@ -56,6 +56,7 @@ _SIGS = {
     "zkv_set_miller_segments": (C.c_int, [C.c_int]),
     "zkv_set_normalised_lines": (C.c_int, [C.c_int]),
     "zkv_launch_count": (C.c_ulonglong, []),
+    "zkv_wave_proofs": (C.c_longlong, [C.c_int, C.c_int]),
     "zkv_imad_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 EXPORTS = tuple(_SIGS)

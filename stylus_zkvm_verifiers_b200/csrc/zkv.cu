@@ -219,7 +219,7 @@ static int g_normalised_lines = 1;      // verification path: gamma / delta line
 extern "C" int zkv_set_normalised_lines(int on) { int old = g_normalised_lines; if (on == 0 || on == 1) g_normalised_lines = on; return old; }
 static int g_miller_segments = 8;       // > 1: the verification Miller loop runs as that many segment kernels per chunk (state in HBM between them)
 extern "C" int zkv_set_miller_segments(int s) { int old = g_miller_segments; if (s >= 1 && s <= 16) g_miller_segments = s; return old; }
-static int g_overlap_chunks = 2;
+static int g_overlap_chunks = 4;
 static std::atomic<unsigned long long> g_launches{0};   // kernels launched by the verification chains since load (bench.py's gpu_launches)
 extern "C" unsigned long long zkv_launch_count(void) { return g_launches.load(); }
 extern "C" int zkv_set_overlap(int chunks) { int old = g_overlap_chunks; if (chunks >= 1 && chunks <= 64) g_overlap_chunks = chunks; return old; }
@@ -784,6 +784,17 @@ extern "C" int zkv_last_stage_ms(const void* handle_vk, int device, float* out, 
 extern "C" const void* zkv_risc0_vk(const zkv_risc0* h) { return h ? h->vk : nullptr; }
 extern "C" const void* zkv_sp1_vk(const zkv_sp1* h) { return h ? h->vk : nullptr; }
 
+// proofs in one full wave of a heavy kernel on `device` (SMs x resident blocks per SM x threads per block): 0 = k_miller_norm, 1 = k_final_exp
+extern "C" long long zkv_wave_proofs(int device, int kernel) {
+    if (zkv_device_count() <= device || device < 0) return fail(ZKV_ERR_CUDA, "no such CUDA device");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(ZKV_ERR_CUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(ZKV_ERR_CUDA, "cudaGetDeviceProperties failed");
+    int per_sm = 0;
+    cudaError_t e = kernel == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_miller_norm, ZKV_HTPB, 0)
+                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_final_exp, ZKV_HTPB, 0);
+    if (e != cudaSuccess) return fail(ZKV_ERR_CUDA, cudaGetErrorString(e));
+    return (long long)prop.multiProcessorCount * per_sm * ZKV_HTPB;
+}
 extern "C" int zkv_imad_peak(int device, double* wide_per_s, double* fpmul_per_s) {
     if (zkv_device_count() <= device || device < 0) return fail(ZKV_ERR_CUDA, "no such CUDA device");
     CK(cudaSetDevice(device));

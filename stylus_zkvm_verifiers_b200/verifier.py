@@ -301,6 +301,14 @@ def set_overlap(chunks):
     return N.lib().zkv_set_overlap(int(chunks))
 
 
+def wave_proofs(device, kernel):
+    """Proofs in one full wave of the verification Miller-loop kernel (kernel 0) or the final exponentiation (kernel 1) on `device`."""
+    w = int(N.lib().zkv_wave_proofs(int(device), int(kernel)))
+    if w <= 0:
+        N.check(w if w < 0 else N.ZKV_ERR_CUDA)
+    return w
+
+
 def launch_count():
     """Kernels launched by the verification chains since the library was loaded."""
     return int(N.lib().zkv_launch_count())

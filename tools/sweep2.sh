@@ -1,14 +1,12 @@
+#!/bin/bash
+# tuning sweep on the GPU box: tools/sweep2.sh "lib|bench flags" ...   (lib = default or a variant build under the package directory)
 cd /root/repo
-run() { python bench.py --steps 5 --warmup 3 --no-cpu-baseline "$@" 2>/dev/null | python -c "
+for cfg in "$@"; do
+  IFS='|' read lib flags <<< "$cfg"
+  if [ "$lib" = "default" ]; then unset ZKV_LIB; else export ZKV_LIB=/root/repo/stylus_zkvm_verifiers_b200/$lib; fi
+  python bench.py --steps 5 --warmup 3 --no-cpu-baseline $flags 2>/dev/null | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
-        d = json.loads(l); print('$*', round(d['value']), round(d['e2e']['value']), round(d['ms_per_step'], 2), d['gpu_launches'])"; }
-run --chunks 2 --segments 8
-run --chunks 2 --segments 16
-run --chunks 3 --segments 8
-run --chunks 4 --segments 8
-run --chunks 4 --segments 16
-run --chunks 2 --segments 4
-run --n 131072
-run --n 262144
+        d = json.loads(l); print('$cfg', round(d['value']), round(d['e2e']['value']), round(d['ms_per_step'], 2), {k: round(v, 2) for k, v in d['stage_ms'].items()})"
+done
