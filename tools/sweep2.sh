@@ -4,7 +4,7 @@ cd /root/repo
 for cfg in "$@"; do
   IFS='|' read lib flags <<< "$cfg"
   if [ "$lib" = "default" ]; then unset ZKV_LIB; else export ZKV_LIB=/root/repo/stylus_zkvm_verifiers_b200/$lib; fi
-  python bench.py --steps 5 --warmup 3 --no-cpu-baseline $flags 2>/dev/null | python -c "
+  python bench.py --steps ${STEPS:-5} --warmup 3 --no-cpu-baseline $flags 2>/dev/null | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
