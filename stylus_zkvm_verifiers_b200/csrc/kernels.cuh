@@ -200,6 +200,15 @@ struct MillerArgs {
 #ifndef ZKV_MINBLOCKS_MILLER
 #define ZKV_MINBLOCKS_MILLER 3
 #endif
+#ifndef ZKV_HTPB_MILLER
+#define ZKV_HTPB_MILLER ZKV_HTPB
+#endif
+#ifndef ZKV_HTPB_FE
+#define ZKV_HTPB_FE ZKV_HTPB
+#endif
+#ifndef ZKV_MINBLOCKS_FE
+#define ZKV_MINBLOCKS_FE ZKV_MINBLOCKS
+#endif
 __global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_miller(int n, MillerArgs a, const uint8_t* flags, fp12* out) {
     int i0 = blockIdx.x * blockDim.x + threadIdx.x;
     int i = i0 < n ? i0 : n - 1;                      // surplus threads redo the last proof (every thread reaches every rendezvous)
@@ -218,7 +227,7 @@ __global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_miller(int n, Mille
 
 // K6 for the verification entry points: pairs (A', B), (vk_x, gamma), (C, delta) with the NORMALISED gamma / delta tables (bn254.cuh),
 // times the per-key constant Miller(alpha, beta).  Same launch shape and flag conventions as k_miller.
-__global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS_MILLER) k_miller_norm(int n, MillerArgs a, const uint8_t* flags, fp12* out) {
+__global__ void __launch_bounds__(ZKV_HTPB_MILLER, ZKV_MINBLOCKS_MILLER) k_miller_norm(int n, MillerArgs a, const uint8_t* flags, fp12* out) {
     int i0 = blockIdx.x * blockDim.x + threadIdx.x;
     int i = i0 < n ? i0 : n - 1;
     uint8_t fl = flags[i];
@@ -238,7 +247,7 @@ __global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS_MILLER) k_miller_norm(
 
 // Segment form of k_miller_norm: digits d_hi .. d_lo of the loop; f (in `fio`) and R (in `rst`) are carried in HBM between segments, the
 // slopes of the two fixed pairs are computed by the first segment and kept in `sl` (4 Fp per proof).
-__global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS_MILLER) k_miller_norm_seg(int n, MillerArgs a, const uint8_t* flags, fp12* fio, g2j* rst, fp* sl,
+__global__ void __launch_bounds__(ZKV_HTPB_MILLER, ZKV_MINBLOCKS_MILLER) k_miller_norm_seg(int n, MillerArgs a, const uint8_t* flags, fp12* fio, g2j* rst, fp* sl,
                                                                               int d_hi, int d_lo, int first, int last) {
     int i0 = blockIdx.x * blockDim.x + threadIdx.x;
     int i = i0 < n ? i0 : n - 1;
@@ -267,7 +276,7 @@ __global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS_MILLER) k_miller_norm_
 }
 
 // K7 + K8: final exponentiation, is-one test and status byte
-__global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_final_exp(int n, const fp12* in, const uint8_t* flags, uint8_t* status, uint8_t* gt_out, int pairing_mode) {
+__global__ void __launch_bounds__(ZKV_HTPB_FE, ZKV_MINBLOCKS_FE) k_final_exp(int n, const fp12* in, const uint8_t* flags, uint8_t* status, uint8_t* gt_out, int pairing_mode) {
     int i0 = blockIdx.x * blockDim.x + threadIdx.x;
     int i = i0 < n ? i0 : n - 1;
     uint8_t fl = flags[i];
@@ -285,7 +294,7 @@ __global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_final_exp(int n, co
 }
 // Staged form of k_final_exp (bn254.cuh final_exp_stage0..3): the state (f, x, y, z, t1; slot 1 first holds t = f^u) lives in `st`, five
 // Fp12 per proof, so that the three exponentiations by u of different chunks can interleave.  Stage 3 writes the status like k_final_exp.
-__global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_final_exp_stage(int n, int stage, const fp12* in, fp12* st, const uint8_t* flags, uint8_t* status) {
+__global__ void __launch_bounds__(ZKV_HTPB_FE, ZKV_MINBLOCKS_FE) k_final_exp_stage(int n, int stage, const fp12* in, fp12* st, const uint8_t* flags, uint8_t* status) {
     int i0 = blockIdx.x * blockDim.x + threadIdx.x;
     int i = i0 < n ? i0 : n - 1;
     const bool w = i0 < n;

@@ -267,16 +267,16 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
         const int S = g_miller_segments, top = ZKV_ATE_NAF_LEN - 2;           // digits top .. 0 in S nearly equal runs
         for (int k = 0; k < S; k++) {
             int hi = top - (top + 1) * k / S, lo = top - (top + 1) * (k + 1) / S + 1;
-            k_miller_norm_seg<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, a, flags, c->f + o, c->rst + o, c->sl + 4 * o, hi, lo, k == 0, k == S - 1);
+            k_miller_norm_seg<<<nblk(m, ZKV_HTPB_MILLER), ZKV_HTPB_MILLER, 0, s>>>(m, a, flags, c->f + o, c->rst + o, c->sl + 4 * o, hi, lo, k == 0, k == S - 1);
         }
         nl += S - 1;
-    } else if (norm) k_miller_norm<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, a, flags, c->f + o);
+    } else if (norm) k_miller_norm<<<nblk(m, ZKV_HTPB_MILLER), ZKV_HTPB_MILLER, 0, s>>>(m, a, flags, c->f + o);
     else k_miller<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, a, flags, c->f + o);
     if (timed) CK(cudaEventRecord(c->ev[4], s));
     if (g_final_exp_stages && !timed && c->fes && c->fes_cap >= o + (size_t)m) {
-        for (int st = 0; st < 4; st++) k_final_exp_stage<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, st, c->f + o, c->fes + 5 * o, flags, j.d_status + jo);
+        for (int st = 0; st < 4; st++) k_final_exp_stage<<<nblk(m, ZKV_HTPB_FE), ZKV_HTPB_FE, 0, s>>>(m, st, c->f + o, c->fes + 5 * o, flags, j.d_status + jo);
         nl += 3;
-    } else k_final_exp<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, c->f + o, flags, j.d_status + jo, nullptr, 0);
+    } else k_final_exp<<<nblk(m, ZKV_HTPB_FE), ZKV_HTPB_FE, 0, s>>>(m, c->f + o, flags, j.d_status + jo, nullptr, 0);
     if (timed) CK(cudaEventRecord(c->ev[5], s));
     g_launches += nl + 2;                   // + Miller loop (first or only kernel) + final exponentiation (first or only kernel)
     CK(cudaGetLastError());
@@ -645,7 +645,7 @@ static int pairing4_chain(DevCtx* c, const zkv_vk* vk, size_t o, int n, const ui
     k_miller<<<nblk(n, ZKV_HTPB), ZKV_HTPB, 0, s>>>(n, a, flags, c->f + o);
     if (timed) CK(cudaEventRecord(c->ev[4], s));
     if (d_miller) k_f12_to_bytes<<<nblk(n), TPB, 0, s>>>(n, c->f + o, d_miller + o * 384);
-    k_final_exp<<<nblk(n, ZKV_HTPB), ZKV_HTPB, 0, s>>>(n, c->f + o, flags, d_ok + o, d_gt ? d_gt + o * 384 : nullptr, 1);
+    k_final_exp<<<nblk(n, ZKV_HTPB_FE), ZKV_HTPB_FE, 0, s>>>(n, c->f + o, flags, d_ok + o, d_gt ? d_gt + o * 384 : nullptr, 1);
     if (timed) CK(cudaEventRecord(c->ev[5], s));
     CK(cudaGetLastError());
     return 0;
@@ -790,10 +790,10 @@ extern "C" long long zkv_wave_proofs(int device, int kernel) {
     if (cudaSetDevice(device) != cudaSuccess) return fail(ZKV_ERR_CUDA, "cudaSetDevice failed");
     cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(ZKV_ERR_CUDA, "cudaGetDeviceProperties failed");
     int per_sm = 0;
-    cudaError_t e = kernel == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_miller_norm, ZKV_HTPB, 0)
-                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_final_exp, ZKV_HTPB, 0);
+    cudaError_t e = kernel == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_miller_norm, ZKV_HTPB_MILLER, 0)
+                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_final_exp, ZKV_HTPB_FE, 0);
     if (e != cudaSuccess) return fail(ZKV_ERR_CUDA, cudaGetErrorString(e));
-    return (long long)prop.multiProcessorCount * per_sm * ZKV_HTPB;
+    return (long long)prop.multiProcessorCount * per_sm * (kernel == 0 ? ZKV_HTPB_MILLER : ZKV_HTPB_FE);
 }
 extern "C" int zkv_imad_peak(int device, double* wide_per_s, double* fpmul_per_s) {
     if (zkv_device_count() <= device || device < 0) return fail(ZKV_ERR_CUDA, "no such CUDA device");

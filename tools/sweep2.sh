@@ -8,5 +8,5 @@ for cfg in "$@"; do
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
-        d = json.loads(l); print('$cfg', round(d['value']), round(d['e2e']['value']), round(d['ms_per_step'], 2), {k: round(v, 2) for k, v in d['stage_ms'].items()})"
+        d = json.loads(l); print('$cfg', round(d['value']), round(d['e2e']['value']), round(d['ms_per_step'], 2), {k: round(v, 2) for k, v in d['stage_ms'].items()}, 'wave', d['roofline']['launch']['proofs'], round(d['roofline']['launch']['ms'], 2), d['roofline']['final_exp_launch']['proofs'], round(d['roofline']['final_exp_launch']['ms'], 2))"
 done
