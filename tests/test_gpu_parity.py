@@ -456,3 +456,27 @@ def test_segmented_miller_loop_matches(Z, gpu, fx):
                 Z.set_final_exp_stages(prev_fe)
     finally:
         Z.set_miller_segments(prev)
+
+
+@pytest.mark.gpu
+def test_launch_counter_and_wave_size(Z, gpu, fx):
+    """zkv_launch_count counts every kernel of the verification chains (bench.py's gpu_launches); zkv_wave_proofs is SMs x resident blocks
+    x 128 threads for the Miller (three blocks per SM) and final-exponentiation (two) kernels."""
+    import torch
+    from stylus_zkvm_verifiers_b200 import synth as S
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    assert Z.wave_proofs(0, 0) == sms * 3 * 128 and Z.wave_proofs(0, 1) == sms * 2 * 128
+    vk = S.make_vk(gpu, 0, 6, 0xB200000D)
+    kv = Z.VerificationKey(0, vk.alpha, vk.beta, vk.gamma, vk.delta, vk.ic)
+    v = Z.RiscZeroVerifier(kv); v.initialize(fx["control_root"], fx["bn254_control_id"])
+    small = S.make_risc0_batch(gpu, vk, v.get_selector(), fx["control_root"], fx["bn254_control_id"], fx["sys0"], 64, 0xB200000D, pool=8)
+    c0 = Z.launch_count()
+    assert set(v.verify_batch(small.seals, small.image_ids, small.journals).tolist()) == {0}
+    assert Z.launch_count() - c0 == 6                      # one serial chain: decode, signals, vk_x, G2 check, Miller loop, final exponentiation
+    n = 8192 + 300
+    big = S.make_risc0_batch(gpu, vk, v.get_selector(), fx["control_root"], fx["bn254_control_id"], fx["sys0"], n, 0xB200000E, pool=8)
+    chunks, segs, fe = Z.set_overlap(0), Z.set_miller_segments(0), Z.set_final_exp_stages(-1)     # out-of-range arguments read the settings
+    c0 = Z.launch_count()
+    assert set(v.verify_batch(big.seals, big.image_ids, big.journals).tolist()) == {0}
+    per_chain = 4 + segs + (4 if fe else 1)
+    assert Z.launch_count() - c0 == chunks * per_chain
