@@ -480,3 +480,40 @@ def test_launch_counter_and_wave_size(Z, gpu, fx):
     assert set(v.verify_batch(big.seals, big.image_ids, big.journals).tolist()) == {0}
     per_chain = 4 + segs + (4 if fe else 1)
     assert Z.launch_count() - c0 == chunks * per_chain
+
+
+def test_concurrent_calls_on_shared_and_separate_handles(Z, gpu, fx):
+    """SURVEY 8b, threading row: handles are immutable after create and the library serialises the calls of one device, so host threads
+    that call one handle (or two handles of different keys) at the same time must each get the oracle's status bytes."""
+    import threading
+    from stylus_zkvm_verifiers_b200 import synth as S
+    vk = S.make_vk(gpu, 0, 6, 0xB2000011)
+    kv = Z.VerificationKey(0, vk.alpha, vk.beta, vk.gamma, vk.delta, vk.ic)
+    v = Z.RiscZeroVerifier(kv); v.initialize(fx["control_root"], fx["bn254_control_id"])
+    ro = O.Risc0Oracle(oracle_vk(vk)); ro.initialize(fx["control_root"], fx["bn254_control_id"])
+    svk = S.make_vk(gpu, 1, 3, 0xB2000012)
+    sv = Z.Sp1Verifier(Z.VerificationKey(1, svk.alpha, svk.beta, svk.gamma, svk.delta, svk.ic))
+    jobs = []
+    for t in range(3):
+        b = S.make_risc0_batch(gpu, vk, v.get_selector(), fx["control_root"], fx["bn254_control_id"], fx["sys0"], 200 + 37 * t, 0xB2000013 + t, pool=16)
+        S.mutate_risc0(b, gpu, S.SplitMix64(0xB2000020 + t))
+        want = ro.verify_batch(b.seals, b.image_ids, b.journals)
+        jobs.append((lambda b=b: v.verify_batch(b.seals, b.image_ids, b.journals), want))
+    sb = S.make_sp1_batch(gpu, svk, 256, 0xB2000016, pool=16)
+    S.mutate_sp1(sb, gpu, S.SplitMix64(0xB2000017))
+    jobs.append((lambda: sv.verify_batch(sb.vkeys, sb.public_values, sb.proofs),
+                 O.sp1_verify_batch(oracle_vk(svk), S.SP1_SELECTOR, sb.vkeys, sb.public_values, sb.proofs)))
+    got, errs = [None] * len(jobs), []
+
+    def run(i):
+        try:
+            for _ in range(3):
+                got[i] = jobs[i][0]()
+                assert got[i].tolist() == jobs[i][1].tolist(), "thread %d: status bytes differ from the oracle's" % i
+        except Exception as e:                                 # surfaced in the main thread below
+            errs.append(e)
+
+    th = [threading.Thread(target=run, args=(i,)) for i in range(len(jobs))]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert not errs, errs
+    assert all(0 < int((w == 0).sum()) < len(w) for _, w in jobs)
