@@ -313,8 +313,8 @@ def main():
         "metric": "groth16_verifies_per_sec", "value": value, "unit": "verifies/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u256 (8x32-bit Montgomery limbs, IMAD.WIDE.U32)", "data": "synthetic",
-        "config": {"workload": "configs[1]: 2^%d synthetic %s-shape Groth16 proofs per GPU per step (%d public inputs, fixed random vk, trapdoor-simulated, all valid)" %
-                   (n.bit_length() - 1, "RISC Zero" if args.shape == "risc0" else "SP1 v5", 5 if args.shape == "risc0" else 2),
+        "config": {"workload": "%s: 2^%d synthetic %s-shape Groth16 proofs per GPU per step (%d public inputs, fixed random vk, trapdoor-simulated, all valid)" %
+                   ("configs[1]" if args.shape == "risc0" else "configs[2] shape", n.bit_length() - 1, "RISC Zero" if args.shape == "risc0" else "SP1 v5", 5 if args.shape == "risc0" else 2),
                    "proofs_per_gpu": n, "l2": "flushed between timed steps (256 MiB fill)", "sharding": "contiguous proof ranges, no collective",
                    "overlap": "%d chunks per device batch on side streams (stage_ms: serial single-chain pass over all proofs; roofline: serial single-chain launches of a whole number of waves)" % chunks},
         "e2e": {"value": total / e2e_s, "unit": "verifies/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": n},
