@@ -16,7 +16,7 @@ def main():
     ap.add_argument("--minutes", type=float, default=5.0)
     ap.add_argument("--batch", type=int, default=1 << 16)
     ap.add_argument("--window", type=int, default=1024)
-    ap.add_argument("--seed", type=int, default=0xB2000004)
+    ap.add_argument("--seed", type=lambda s: int(s, 0), default=0xB2000004)
     a = ap.parse_args()
     import oracle_lib as O
     import stylus_zkvm_verifiers_b200 as Z
