@@ -55,3 +55,12 @@ def test_error_payloads():
     p = E.SelectorMismatch(b"\x01\x02\x03\x04", b"\x9f\x39\x69\x6c").payload
     assert len(p) == 68 and p[4:8] == b"\x01\x02\x03\x04" and p[8:36] == bytes(28) and p[36:40] == b"\x9f\x39\x69\x6c"
     assert E.WrongVerifierSelector(b"abcd", b"efgh").payload[:4] == E.keccak256(b"WrongVerifierSelector(bytes4,bytes4)")[:4]
+
+
+def test_tools_and_bench_parse():
+    """bench.py and the measurement tools under tools/ are run on the GPU box only: keep them at least syntactically valid here."""
+    import ast, glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for path in [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")] + sorted(glob.glob(os.path.join(root, "tools", "*.py"))):
+        with open(path) as f:
+            ast.parse(f.read(), filename=path)
