@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--fe-stages", type=int, default=-1, help="staged final exponentiation for chunked batches: 1 on, 0 off (-1 = library default)")
     ap.add_argument("--segments", type=int, default=0, help="Miller loop segments per chunk (0 = library default)")
     ap.add_argument("--chunks", type=int, default=0, help="stream-overlap chunks per device batch (0 = library default)")
+    ap.add_argument("--layout", type=int, default=-1, help="1 = shared-memory-resident lazily reduced kernels (default), 0 = the round-1 thread-stack kernels (A/B)")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
@@ -231,14 +232,16 @@ def main():
         torch.cuda.synchronize()
 
     if args.exact_lines:
-        Z.set_normalised_lines(0)
+        v.tune("normalised_lines", 0)
     if args.fe_stages >= 0:
-        Z.set_final_exp_stages(args.fe_stages)
+        v.tune("final_exp_stages", args.fe_stages)
     if args.segments:
-        Z.set_miller_segments(args.segments)
+        v.tune("miller_segments", args.segments)
     if args.chunks:
-        Z.set_overlap(args.chunks)
-    chunks = Z.set_overlap(0)                    # 0 is out of range: reads the current value
+        v.tune("overlap", args.chunks)
+    if args.layout >= 0:
+        v.tune("layout", args.layout)
+    chunks, layout = v.tune("overlap"), v.tune("layout")
     for _ in range(max(args.warmup, 3)):
         launch(d_st, sp)
     torch.cuda.synchronize()
@@ -247,7 +250,7 @@ def main():
 
     # per-kernel durations for the roofline: one chain on one stream (no overlap between chunks), CUDA events around every stage
     stage_sum, stage_reps = {}, 3
-    Z.set_overlap(1)
+    v.tune("overlap", 1)
     launch(d_st, sp); torch.cuda.synchronize()
     for k in range(stage_reps):
         flush_ = torch.empty(256 << 20, dtype=torch.uint8, device="cuda").fill_(k); del flush_
@@ -260,7 +263,7 @@ def main():
         w = Z.wave_proofs(dev, kernel)
         return (n // w) * w if n >= w else n
     wave_ms, wave_n = {}, {}
-    for name, kernel in (("miller", 0), ("final_exp", 1)):
+    for name, kernel in (("miller", 0 if layout else 2), ("final_exp", 1 if layout else 3)):
         m = whole_waves(kernel); wave_n[name] = m; acc = 0.0
         launch(d_st, sp, m); torch.cuda.synchronize()
         for k in range(stage_reps):
@@ -268,7 +271,7 @@ def main():
             launch(d_st, sp, m); torch.cuda.synchronize()
             acc += v.stage_ms(dev)[name] / stage_reps
         wave_ms[name] = acc
-    Z.set_overlap(chunks)
+    v.tune("overlap", chunks)
     launch(d_st, sp); torch.cuda.synchronize()
 
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -308,7 +311,7 @@ def main():
     fe_ms, fe_n = wave_ms["final_exp"], wave_n["final_exp"]
     mac_miller = miller_n * W_MILLER3_M * M_MAC32
     serial_miller_ms = stage_sum.get("miller", 0.0)
-    miller_kernel = "k_miller" if args.exact_lines else "k_miller_norm"    # verification path: normalised gamma / delta lines by default
+    miller_kernel = "k_miller" if args.exact_lines else ("k_miller_lz" if layout else "k_miller_norm")    # verification path: normalised gamma / delta lines by default
     line = {
         "metric": "groth16_verifies_per_sec", "value": value, "unit": "verifies/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -141,33 +141,41 @@ int zkv_fp_mul_batch(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out,
 /* Fp12 tower operations of the pairing kernels on byte operands (n x 384 B = 12 x BE-32, tower order c0.c0.c0, c0.c0.c1, ...), for
  * parity tests against the oracle: op 0 a*b, 1 a^2, 2 a * line(l0,l3,l4) with the line in b's first three Fp2 slots, 3 cyclotomic
  * squaring, 4 inverse, 5/6/7 Frobenius^1/2/3, 8 final exponentiation, 9 Miller loop of the single pair (P, Q) held in b's first six words (P.x, P.y, Q in
- * wire order; a is ignored).  b may be NULL for the unary operations. */
+ * wire order; a is ignored).  b may be NULL for the unary operations.  op 16 + k (k = 0..8) runs operation k in the shared-memory-resident
+ * lazily reduced form the verification kernels use (csrc/lazy.cuh); op 25 = a * (1 + (c3 + c4 v) w), the normalised-line product, with
+ * c3, c4 in b's first two Fp2; op 26 = the verification kernels' Miller loop on the single pair of op 9 (fixed pairs switched off). */
 int zkv_fp12_op_batch(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out, int device);
 /* G2 membership kernel alone: out[i] = 1 in G2 / 0 on twist but wrong subgroup / 2 invalid encoding or off twist */
 int zkv_g2_check_batch(const uint8_t* g2s, size_t n, uint8_t* out, int device);
 /* timing of the stage kernels of the last *_device / host call on `device`, milliseconds, for bench.py:
  * [0] decode+hash [1] vk_x [2] g2 check [3] miller [4] final exp ; returns number of entries */
 int zkv_last_stage_ms(const void* handle_vk, int device, float* out, int cap);
-/* A device batch is cut into `chunks` pieces whose kernel chains run on side streams of the device context, so the partial last wave of
- * one kernel is back-filled by blocks of another (default 4; batches under 8192 proofs are never cut).  chunks = 1 runs one chain on the
- * main stream and records the per-stage events zkv_last_stage_ms reads.  Process-wide; returns the previous value. */
-int zkv_set_overlap(int chunks);
-/* Verification path only: use the per-key normalised gamma / delta line tables (lines scaled by a subfield element so that their first
- * coefficient is 1; the final exponentiation output and every status byte are unchanged).  On by default; 0 runs
- * the unscaled lines of the pairing service instead (A/B measurements, parity tests).  Returns the previous setting. */
-int zkv_set_normalised_lines(int on);
-/* Verification path: run the Miller loop of every chunk as `segments` kernels (f and R carried in HBM between them) so that the kernels of
- * different chunks interleave at a finer grain than a whole loop (default 8; measured -2.6 % per step at 2^16 proofs).  Single-chain batches
- * (under 8192 proofs, or zkv_set_overlap(1)) always use the one-kernel form.  Returns the previous value. */
-int zkv_set_miller_segments(int segments);
-/* Verification path: chunked batches of at most 2^18 proofs run the final exponentiation as four stage kernels with their state (five
- * Fp12 per proof) in HBM, for the same reason as zkv_set_miller_segments.  On by default; returns the previous setting. */
-int zkv_set_final_exp_stages(int on);
+/* Tuning of ONE key handle (every verifier handle built on that key sees it; there is no process-wide setting).  `handle_vk` is a
+ * zkv_vk* or what zkv_risc0_vk / zkv_sp1_vk return.  Returns the previous value (value = ZKV_TUNE_QUERY only reads it), < 0 on error.
+ * None of the options changes a status byte or a final-exponentiation value (tests/test_gpu_parity.py).
+ *   ZKV_TUNE_OVERLAP (1..64, default 4): a device batch is cut into that many pieces whose kernel chains run on side streams, so the
+ *     partial last wave of one kernel is back-filled by blocks of another; batches under 8192 proofs are never cut; 1 = one chain on
+ *     the main stream with the per-stage events zkv_last_stage_ms reads.
+ *   ZKV_TUNE_NORMALISED_LINES (0/1, default 1): verification path uses the per-key normalised gamma / delta line tables (first
+ *     coefficient scaled to 1 by a subfield element: 10 instead of 13 Fp2 products per line); 0 = the unscaled lines of the pairing service.
+ *   ZKV_TUNE_MILLER_SEGMENTS (1..16, default 8): chunked batches run the Miller loop as that many kernels (f, R carried in HBM).
+ *   ZKV_TUNE_FINAL_EXP_STAGES (0/1, default 1): chunked batches run the final exponentiation as four stage kernels (state in HBM).
+ *   ZKV_TUNE_LAYOUT (0/1, default 1): 1 = shared-memory-resident lazily reduced Miller / final-exponentiation kernels (two blocks of
+ *     128 threads per SM, 28 Fp slots of shared memory per proof), 0 = the round-1 kernels (thread stack, three / two blocks per SM);
+ *     kept for A/B measurements. */
+#define ZKV_TUNE_OVERLAP 0
+#define ZKV_TUNE_NORMALISED_LINES 1
+#define ZKV_TUNE_MILLER_SEGMENTS 2
+#define ZKV_TUNE_FINAL_EXP_STAGES 3
+#define ZKV_TUNE_LAYOUT 4
+#define ZKV_TUNE_QUERY (-1)
+int zkv_vk_tune(const void* handle_vk, int option, int value);
 /* Kernels launched by the verification chains (decode .. final exponentiation, every chunk, segment and stage) since the library was
  * loaded; bench.py reports the difference over its timed region as gpu_launches. */
 unsigned long long zkv_launch_count(void);
 /* Proofs in one full wave of a heavy kernel on `device` (SM count x resident blocks per SM x 128 threads): kernel 0 = the verification
- * Miller loop, 1 = the final exponentiation.  bench.py times whole-wave launches for its roofline figures.  Negative = error. */
+ * Miller loop, 1 = the final exponentiation (shared-memory layout); 2, 3 = the same two in the round-1 layout.  bench.py times
+ * whole-wave launches for its roofline figures.  Negative = error. */
 long long zkv_wave_proofs(int device, int kernel);
 /* integer-pipe microbenchmark (roofline denominator): returns measured IMAD.WIDE.U32 results/s and
  * Fp-multiplications/s on `device` */

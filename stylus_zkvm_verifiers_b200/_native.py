@@ -9,6 +9,8 @@ SO_PATH = os.environ.get("ZKV_LIB") or os.path.join(HERE, "libzkv_b200.so")   # 
 ZKV_OK, ZKV_INVALID_INITIALIZATION, ZKV_INVALID_PROOF_DATA, ZKV_SELECTOR_MISMATCH, ZKV_VERIFICATION_FAILED = range(5)
 ZKV_ERR_ARG, ZKV_ERR_CUDA, ZKV_ERR_STATE = -1, -2, -3
 ZKV_VM_RISC0, ZKV_VM_SP1 = 0, 1
+TUNE = {"overlap": 0, "normalised_lines": 1, "miller_segments": 2, "final_exp_stages": 3, "layout": 4}     # ZKV_TUNE_* of zkv.h
+ZKV_TUNE_QUERY = -1
 
 _P = C.c_void_p
 _SIGS = {
@@ -51,10 +53,7 @@ _SIGS = {
     "zkv_last_stage_ms": (C.c_int, [_P, C.c_int, _P, C.c_int]),
     "zkv_risc0_vk": (_P, [_P]),
     "zkv_sp1_vk": (_P, [_P]),
-    "zkv_set_overlap": (C.c_int, [C.c_int]),
-    "zkv_set_final_exp_stages": (C.c_int, [C.c_int]),
-    "zkv_set_miller_segments": (C.c_int, [C.c_int]),
-    "zkv_set_normalised_lines": (C.c_int, [C.c_int]),
+    "zkv_vk_tune": (C.c_int, [_P, C.c_int, C.c_int]),
     "zkv_launch_count": (C.c_ulonglong, []),
     "zkv_wave_proofs": (C.c_longlong, [C.c_int, C.c_int]),
     "zkv_imad_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -5,6 +5,7 @@
 // risc0/verifier.rs:146-197, sp1/verifier.rs:58-111; precompile semantics per EIP-196/197.
 #pragma once
 #include "bn254.cuh"
+#include "lazy.cuh"
 #include "sha256.cuh"
 
 namespace zkv {
@@ -320,6 +321,53 @@ __global__ void __launch_bounds__(ZKV_HTPB_FE, ZKV_MINBLOCKS_FE) k_final_exp_sta
         status[i] = f12_is_one(gt) ? ST_OK : ST_VERIFICATION_FAILED;
     }
 }
+// ---------------------------------------------------------------------------- shared-memory-resident forms of K6 / K7 (csrc/lazy.cuh)
+// Same inputs, outputs and flag conventions as k_miller_norm_seg / k_final_exp_stage; the working set of a proof (f, R, temporaries: 28 Fp
+// slots = 896 B) lives in shared memory, two blocks of LZ_NT = 128 threads per SM, the Fp6-level products are lazily reduced.  The state
+// between segments / stages travels through HBM exactly as in the round-1 kernels.  `sl` must have room for 4 Fp per LAUNCHED thread
+// (surplus threads of the last block park their slopes behind the batch).
+#define LZ_SMEM_BYTES (LZ_SLOTS * 32 * LZ_NT)
+// slopes of the two fixed pairs (g1_slopes2) written to sl[0..3] = xy0, xy1, iy0, iy1; out of line so that its arrays have a frame of their own
+__device__ __noinline__ void lz_slopes_to(fp* sl, const fp* x1, const fp* y1, const fp* x2, const fp* y2, bool off1, bool off2) {
+    fp x12[2] = {*x1, *x2}, y12[2] = {*y1, *y2}, xy[2], iy[2];
+    bool off[2] = {off1, off2};
+    g1_slopes2(xy, iy, x12, y12, off);
+    sl[0] = xy[0]; sl[1] = xy[1]; sl[2] = iy[0]; sl[3] = iy[1];
+}
+__global__ void __launch_bounds__(LZ_NT, 2) k_miller_lz(int n, MillerArgs a, const uint8_t* flags, fp12* fio, g2j* rst, fp* sl, int d_hi, int d_lo, int first, int last) {
+    const int i0 = blockIdx.x * LZ_NT + threadIdx.x, i = i0 < n ? i0 : n - 1;
+    const uint8_t fl = flags[i];
+    uint32_t skip = a.vk_skip;
+    for (int j = 0; j < 3; j++) if (fl & a.skip_bit[j]) skip |= 1u << j;
+    if (fl & (F_INVALID | F_SELMIS)) skip = 0xF;
+    fp* mysl = sl + 4 * (size_t)i0;
+    if (first) lz_slopes_to(mysl, a.px[1] + i, a.py[1] + i, a.px[2] + i, a.py[2] + i, (skip & 2u) != 0, (skip & 4u) != 0);
+    LzMillerIn in;
+    in.px0 = a.px[0] + i; in.py0 = a.py[0] + i; in.qx = a.qx + i; in.qy = a.qy + i; in.sl = mysl; in.nt[0] = a.ntabs[0]; in.nt[1] = a.ntabs[1]; in.var_off = (skip & 1u) != 0;
+    const uint32_t tid = lz_tid();
+    if (first) lz_miller_init(a.qx[i], a.qy[i]);
+    else {
+        lz_ldg12(tid + LZ_F * LZ_SLOT, fio + i);
+        const g2j* R = rst + i;
+        lz_st2(tid + LZ_R * LZ_SLOT, R->x); lz_st2(tid + (LZ_R + 2) * LZ_SLOT, R->y); lz_st2(tid + (LZ_R + 4) * LZ_SLOT, R->z);
+    }
+    lz_miller_norm_seg(in, d_hi, d_lo, last != 0);
+    if (last) { if (a.pre) lz_f12mul_g(tid + LZ_F * LZ_SLOT, tid + LZ_T * LZ_SLOT, tid + LZ_R * LZ_SLOT, a.pre, false); }      // x Miller(alpha, beta); T and R are free now
+    else if (i0 < n) { g2j* R = rst + i; R->x = lz_ld2(tid + LZ_R * LZ_SLOT); R->y = lz_ld2(tid + (LZ_R + 2) * LZ_SLOT); R->z = lz_ld2(tid + (LZ_R + 4) * LZ_SLOT); }
+    if (i0 < n) lz_stg12(fio + i, tid + LZ_F * LZ_SLOT);
+}
+// stages s_lo .. s_hi of the final exponentiation (0..3 = all of it in one launch); st = 6 Fp12 of state per LAUNCHED thread; the last stage writes the status
+__global__ void __launch_bounds__(LZ_NT, 2) k_final_exp_lz(int n, int s_lo, int s_hi, const fp12* in, fp12* st, const uint8_t* flags, uint8_t* status) {
+    const int i0 = blockIdx.x * LZ_NT + threadIdx.x, i = i0 < n ? i0 : n - 1;
+    for (int s = s_lo; s <= s_hi; s++) lz_final_exp_stage(s, in + i, st + 6 * (size_t)i0);
+    if (s_hi < 3 || i0 >= n) return;
+    const uint8_t fl = flags[i];
+    if (fl & (F_INVALID | F_SELMIS)) { status[i] = (fl & F_SELMIS) ? ST_SELECTOR_MISMATCH : ST_VERIFICATION_FAILED; return; }
+    const uint32_t tid = lz_tid();
+    fp one = fp_one(); uint32_t t = 0;
+    for (int k = 0; k < 12; k++) { fp w = lz_ldfp(tid + (LZ_A + k) * LZ_SLOT); for (int j = 0; j < 8; j++) t |= w.v[j] ^ (k == 0 ? one.v[j] : 0u); }
+    status[i] = t == 0 ? ST_OK : ST_VERIFICATION_FAILED;
+}
 // parity hook: one Fp12 tower operation per thread on byte operands (12 x BE-32 each, tower order).
 // op 0: a*b  1: a^2  2: a * line(b.c0.c0, b.c0.c1, b.c0.c2)  3: cyclotomic square  4: 1/a  5..7: Frobenius^(op-4)  8: final exponentiation  9: single-pair Miller loop
 __global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_fp12_op(int n, int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
@@ -343,6 +391,45 @@ __global__ void __launch_bounds__(ZKV_HTPB, ZKV_MINBLOCKS) k_fp12_op(int n, int 
             miller_loop(z, px, py, qx, qy, nullptr, 0, n > (1 << 30) ? 1u : 0u); break; }
     }
     if (i0 < n) f12_to_bytes(out + (size_t)i * 384, z);
+}
+// parity hook for the shared-memory-resident tower (lazy.cuh): the same operations as k_fp12_op (op 0..8) on slots, plus
+// op 9: a * (1 + (c3 + c4 v) w) with c3, c4 = b's first two Fp2 (the normalised line product of the verification loop);
+// op 10: the verification Miller loop (lz_miller_norm_seg, in three segments) of the single pair (P, Q) held in b like k_fp12_op's op 9, the
+// two fixed pairs switched off (zero slopes, all-zero line tables `ztab`): the value must equal k_fp12_op's op 9 bit for bit.
+__global__ void __launch_bounds__(LZ_NT, 2) k_lz_fp12_op(int n, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, fp12* scratch /* 7 Fp12 per launched thread */, const nline_t* ztab) {
+    const int i0 = blockIdx.x * LZ_NT + threadIdx.x, i = i0 < n ? i0 : n - 1;
+    const uint32_t tid = lz_tid(), A = tid + LZ_A * LZ_SLOT, X = tid + LZ_X * LZ_SLOT, Y = tid + LZ_Y * LZ_SLOT, L = tid + LZ_L * LZ_SLOT;
+    fp12* my = scratch + 7 * (size_t)i0;
+    {
+        fp12 y; fp* yw = &y.c0.c0.c0;
+        for (int k = 0; k < 12; k++) {
+            fp t; be32_to_raw(t.v, a + (size_t)i * 384 + 32 * k); fp_to_mont(t, t); lz_stfp(A + k * LZ_SLOT, t);
+            if (b) { be32_to_raw(t.v, b + (size_t)i * 384 + 32 * k); fp_to_mont(yw[k], t); } else yw[k] = fp_zero();
+        }
+        my[6] = y;
+    }
+    switch (op) {
+        case 0: lz_f12mul_g(A, X, Y, my + 6, false); break;
+        case 1: lz_f12sqr(A, X); break;
+        case 2: { fp2 l0 = my[6].c0.c0; lz_st2(L, my[6].c0.c1); lz_st2(L + 2 * LZ_SLOT, my[6].c0.c2); lz_mul_line(A, X, L, l0); break; }
+        case 3: lz_cyc_sqr(A, L); break;
+        case 4: lz_f12inv(A, X, Y); break;
+        case 5: case 6: case 7: lz_frob(A, op - 4); break;
+        case 8: { lz_stg12(my + 6, A); for (int s = 0; s < 4; s++) lz_final_exp_stage(s, my + 6, my); break; }
+        case 9: lz_st2(L, my[6].c0.c0); lz_st2(L + 2 * LZ_SLOT, my[6].c0.c1); lz_mul_nline(A, X, L); break;
+        default: {
+            const fp* yw = &my[6].c0.c0.c0;
+            fp* g = &my[0].c0.c0.c0;                        // per-thread global scratch: px, py, slopes (4 x 0), qx, qy
+            g[0] = yw[0]; g[1] = yw[1]; for (int k = 2; k < 6; k++) g[k] = fp_zero();
+            fp2 qx, qy; qx.c1 = yw[2]; qx.c0 = yw[3]; qy.c1 = yw[4]; qy.c0 = yw[5];
+            fp2* gq = (fp2*)(g + 6); gq[0] = qx; gq[1] = qy;
+            LzMillerIn in; in.px0 = g; in.py0 = g + 1; in.sl = g + 2; in.qx = gq; in.qy = gq + 1; in.nt[0] = ztab; in.nt[1] = ztab; in.var_off = false;
+            lz_miller_init(qx, qy);
+            const int top = ZKV_ATE_NAF_LEN - 2;
+            for (int k = 0; k < 3; k++) lz_miller_norm_seg(in, top - (top + 1) * k / 3, top - (top + 1) * (k + 1) / 3 + 1, k == 2);
+            break; }
+    }
+    if (i0 < n) for (int k = 0; k < 12; k++) fp_to_be32(out + (size_t)i * 384 + 32 * k, lz_ldfp(A + k * LZ_SLOT));
 }
 __global__ void k_f12_to_bytes(int n, const fp12* in, uint8_t* out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <mutex>
@@ -73,11 +74,22 @@ struct DevCtx {
     static constexpr int NAUX = 4;
     cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr, nullptr, nullptr};
+    // The workspace above is shared by every call on this key and device.  Host-buffer calls return only when their work is done; the
+    // *_device calls are asynchronous, so each records `ev_busy` behind its last kernel and every later user of the workspace, on whatever
+    // stream, first waits for it (ctx_acquire).
+    cudaEvent_t ev_busy = nullptr; bool busy = false;
     std::mutex mu;
 };
 
-static int g_final_exp_stages = 1;      // 1: chunked batches run the final exponentiation as four stage kernels (state: 5 Fp12 per proof in HBM)
-extern "C" int zkv_set_final_exp_stages(int on) { int old = g_final_exp_stages; if (on == 0 || on == 1) g_final_exp_stages = on; return old; }
+// Tuning of one key handle (zkv_vk_tune): no process-wide mutable state.  Read once per batch call.
+struct Tuning {
+    std::atomic<int> overlap_chunks{4};     // a device batch is cut into this many kernel chains on side streams
+    std::atomic<int> normalised_lines{1};   // verification path: gamma / delta lines scaled to (1, n3, n4)
+    std::atomic<int> miller_segments{8};    // chunked batches: segment kernels per Miller loop (state in HBM between them)
+    std::atomic<int> final_exp_stages{1};   // chunked batches: the final exponentiation as four stage kernels
+    std::atomic<int> layout{1};             // 1: shared-memory-resident lazily reduced kernels (lazy.cuh); 0: the round-1 thread-stack kernels
+};
+static constexpr size_t PAD = 256;          // workspace slack behind a batch: surplus threads of the last block park their state there
 static int ctx_reserve(DevCtx* c, size_t n, size_t scal_words_per_proof) {
     if (n > c->cap) {
         for (int j = 0; j < 4; j++) { cudaFree(c->px[j]); cudaFree(c->py[j]); }
@@ -85,13 +97,13 @@ static int ctx_reserve(DevCtx* c, size_t n, size_t scal_words_per_proof) {
         c->cap = 0;
         for (int j = 0; j < 4; j++) { CK(cudaMalloc(&c->px[j], n * sizeof(fp))); CK(cudaMalloc(&c->py[j], n * sizeof(fp))); }
         CK(cudaMalloc(&c->qx, n * sizeof(fp2))); CK(cudaMalloc(&c->qy, n * sizeof(fp2))); CK(cudaMalloc(&c->f, n * sizeof(fp12)));
-        CK(cudaMalloc(&c->rst, n * sizeof(g2j))); CK(cudaMalloc(&c->sl, n * 4 * sizeof(fp)));
+        CK(cudaMalloc(&c->rst, n * sizeof(g2j))); CK(cudaMalloc(&c->sl, (n + PAD) * 4 * sizeof(fp)));
         CK(cudaMalloc(&c->flags, n)); CK(cudaMalloc(&c->status, n));
         c->cap = n;
     }
-    if (g_final_exp_stages && n >= 8192 && n <= ((size_t)1 << 18) && n > c->fes_cap) {      // staged final exponentiation: 1.9 KB per proof, bounded to 2^18 proofs (0.5 GB)
+    if (n > c->fes_cap) {      // final-exponentiation state: six Fp12 (2.3 KB) per proof
         cudaFree(c->fes); c->fes = nullptr; c->fes_cap = 0;
-        CK(cudaMalloc(&c->fes, n * 5 * sizeof(fp12))); c->fes_cap = n;
+        CK(cudaMalloc(&c->fes, (n + PAD) * 6 * sizeof(fp12))); c->fes_cap = n;
     }
     size_t need = n * scal_words_per_proof;
     if (need > c->scal_words) { cudaFree(c->scal); c->scal_words = 0; CK(cudaMalloc(&c->scal, need * 4)); c->scal_words = need; }
@@ -104,6 +116,9 @@ static int ctx_stage(DevCtx* c, size_t in_bytes, size_t out_bytes) {
         size_t cap = out_bytes + out_bytes / 4 + 4096; CK(cudaMalloc(&c->d_out, cap)); CK(cudaMallocHost(&c->h_out, cap)); c->d_out_cap = cap; c->h_out_cap = cap; }
     return 0;
 }
+// order stream `s` after the last asynchronous user of the workspace (caller holds c->mu)
+static int ctx_acquire(DevCtx* c, cudaStream_t s) { if (c->busy) CK(cudaStreamWaitEvent(s, c->ev_busy, 0)); return 0; }
+static int ctx_release_async(DevCtx* c, cudaStream_t s) { CK(cudaEventRecord(c->ev_busy, s)); c->busy = true; return 0; }
 static void ctx_free(DevCtx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
@@ -114,6 +129,7 @@ static void ctx_free(DevCtx* c) {
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_join) if (e) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_busy) cudaEventDestroy(c->ev_busy);
     for (auto& a : c->aux) if (a) cudaStreamDestroy(a);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -126,6 +142,7 @@ struct zkv_vk {
     std::vector<uint8_t> ic;
     std::vector<DevCtx*> devs;
     int valid = 1;     // every key point decodes under EIP-196/197 (else each verification's precompile call reverts -> false)
+    mutable Tuning tune;
 };
 static DevCtx* vk_ctx(const zkv_vk* vk, int device) { for (auto* c : vk->devs) if (c->device == device) return c; return nullptr; }
 
@@ -135,7 +152,10 @@ static int vk_build_on(zkv_vk* vk, DevCtx* c) {
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
     for (auto& a : c->aux) CK(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_busy, cudaEventDisableTiming));
     for (auto& e : c->ev_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaFuncSetAttribute(k_miller_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_final_exp_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_BYTES));
     int nt = vk->n_ic - 1;
     CK(cudaMalloc(&c->d_vk, sizeof(VkDev))); CK(cudaMalloc(&c->d_lines, sizeof(line_t) * 3 * ZKV_LINES_PER_G2)); CK(cudaMalloc(&c->d_nlines, sizeof(nline_t) * 2 * ZKV_LINES_PER_G2)); CK(cudaMalloc(&c->d_pre, sizeof(fp12)));
     CK(cudaMalloc(&c->d_tab, sizeof(g1aff) * (size_t)nt * ZKV_WIN_PER_SCALAR * ZKV_WIN_ENTRIES)); CK(cudaMalloc(&c->d_ic0, sizeof(g1aff)));
@@ -213,19 +233,29 @@ __global__ void k_status_all_fail(int n, const uint8_t* flags, uint8_t* status) 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) status[i] = (flags[i] & F_SELMIS) ? ST_SELECTOR_MISMATCH : ST_VERIFICATION_FAILED;
 }
-// Number of chunks a device batch is cut into (each chunk's kernel chain runs on its own side stream).  1 = one chain on the main stream
-// with per-stage events (what bench.py uses for the per-kernel roofline figures).
-static int g_normalised_lines = 1;      // verification path: gamma / delta lines scaled to (1, n3, n4): 10 instead of 13 Fp2 multiplications per line
-extern "C" int zkv_set_normalised_lines(int on) { int old = g_normalised_lines; if (on == 0 || on == 1) g_normalised_lines = on; return old; }
-static int g_miller_segments = 8;       // > 1: the verification Miller loop runs as that many segment kernels per chunk (state in HBM between them)
-extern "C" int zkv_set_miller_segments(int s) { int old = g_miller_segments; if (s >= 1 && s <= 16) g_miller_segments = s; return old; }
-static int g_overlap_chunks = 4;
-static std::atomic<unsigned long long> g_launches{0};   // kernels launched by the verification chains since load (bench.py's gpu_launches)
+static std::atomic<unsigned long long> g_launches{0};   // kernels launched by the verification chains since load (bench.py's gpu_launches; a counter, not a setting)
 extern "C" unsigned long long zkv_launch_count(void) { return g_launches.load(); }
-extern "C" int zkv_set_overlap(int chunks) { int old = g_overlap_chunks; if (chunks >= 1 && chunks <= 64) g_overlap_chunks = chunks; return old; }
+extern "C" int zkv_vk_tune(const void* handle_vk, int option, int value) {
+    const zkv_vk* vk = (const zkv_vk*)handle_vk;
+    if (!vk) return fail(ZKV_ERR_ARG, "zkv_vk_tune: null key");
+    std::atomic<int>* f; int lo, hi;
+    switch (option) {
+        case ZKV_TUNE_OVERLAP: f = &vk->tune.overlap_chunks; lo = 1; hi = 64; break;
+        case ZKV_TUNE_NORMALISED_LINES: f = &vk->tune.normalised_lines; lo = 0; hi = 1; break;
+        case ZKV_TUNE_MILLER_SEGMENTS: f = &vk->tune.miller_segments; lo = 1; hi = 16; break;
+        case ZKV_TUNE_FINAL_EXP_STAGES: f = &vk->tune.final_exp_stages; lo = 0; hi = 1; break;
+        case ZKV_TUNE_LAYOUT: f = &vk->tune.layout; lo = 0; hi = 1; break;
+        default: return fail(ZKV_ERR_ARG, "zkv_vk_tune: unknown option");
+    }
+    if (value == ZKV_TUNE_QUERY) return f->load();
+    if (value < lo || value > hi) return fail(ZKV_ERR_ARG, "zkv_vk_tune: value out of range");
+    return f->exchange(value);
+}
 
 // the kernel chain for proofs [o, o+m) of job j on stream s; stage events only when `timed`
 // jo: offset of the first proof inside the job's buffers, o: offset inside the device workspace
+static const bool g_debug_sync = getenv("ZKV_DEBUG_SYNC") != nullptr;      // diagnostics: synchronise after every kernel of a chain and name the one that failed
+#define DBG(name) do { if (g_debug_sync) { cudaError_t e_ = cudaStreamSynchronize(s); if (e_ != cudaSuccess) return fail(ZKV_ERR_CUDA, std::string(name) + ": " + cudaGetErrorString(e_)); } } while (0)
 static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cudaStream_t s, bool timed) {
     const zkv_vk* vk = j.vk;
     int ns = (j.mode == SIG_GENERIC) ? j.k : 2;
@@ -251,7 +281,9 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
     }
     k_vkx<<<nblk(m), TPB, 0, s>>>(m, scal, ns, nwin, tab, j.base, c->px[2] + o, c->py[2] + o, flags);
     if (timed) CK(cudaEventRecord(c->ev[2], s));
+    DBG("decode / signals / vk_x");
     k_g2_check<<<nblk(m), TPB, 0, s>>>(m, c->qx + o, c->qy + o, flags);
+    DBG("k_g2_check");
     if (timed) CK(cudaEventRecord(c->ev[3], s));
     MillerArgs a; memset(&a, 0, sizeof a);
     a.px[0] = c->px[0] + o; a.py[0] = c->py[0] + o; a.px[1] = c->px[2] + o; a.py[1] = c->py[2] + o; a.px[2] = c->px[3] + o; a.py[2] = c->py[3] + o;
@@ -259,12 +291,23 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
     a.tabs[0] = c->d_lines + 1 * ZKV_LINES_PER_G2; a.tabs[1] = c->d_lines + 2 * ZKV_LINES_PER_G2;
     a.nfixed = 2; a.pre = c->d_pre;
     a.ntabs[0] = c->d_nlines; a.ntabs[1] = c->d_nlines + ZKV_LINES_PER_G2;
-    const bool norm = c->h_vk.norm_ok && g_normalised_lines;
+    const bool norm = c->h_vk.norm_ok && vk->tune.normalised_lines.load();
+    const bool lazy = norm && vk->tune.layout.load();
+    const int segs = vk->tune.miller_segments.load(), stages = vk->tune.final_exp_stages.load();
     int nl = 4;                             // decode, signals, vk_x, G2 check
     a.skip_bit[0] = F_SKIP0; a.skip_bit[1] = F_SKIPX; a.skip_bit[2] = F_SKIPC;
     a.vk_skip = (uint8_t)((c->h_vk.g2_inf[1] ? 2 : 0) | (c->h_vk.g2_inf[2] ? 4 : 0));
-    if (norm && g_miller_segments > 1 && !timed) {      // a timed single chain (per-stage roofline pass, small batches) runs the one-kernel form
-        const int S = g_miller_segments, top = ZKV_ATE_NAF_LEN - 2;           // digits top .. 0 in S nearly equal runs
+    const int top = ZKV_ATE_NAF_LEN - 2;    // digits top .. 0 of the loop
+    if (lazy) {                             // shared-memory-resident kernels (lazy.cuh): segments when chunked, one launch otherwise
+        const int S = (segs > 1 && !timed) ? segs : 1;
+        for (int k = 0; k < S; k++) {
+            int hi = top - (top + 1) * k / S, lo = top - (top + 1) * (k + 1) / S + 1;
+            k_miller_lz<<<nblk(m, LZ_NT), LZ_NT, LZ_SMEM_BYTES, s>>>(m, a, flags, c->f + o, c->rst + o, c->sl + 4 * o, hi, lo, k == 0, k == S - 1);
+            DBG("k_miller_lz");
+        }
+        nl += S - 1;
+    } else if (norm && segs > 1 && !timed) {      // a timed single chain (per-stage roofline pass, small batches) runs the one-kernel form
+        const int S = segs;
         for (int k = 0; k < S; k++) {
             int hi = top - (top + 1) * k / S, lo = top - (top + 1) * (k + 1) / S + 1;
             k_miller_norm_seg<<<nblk(m, ZKV_HTPB_MILLER), ZKV_HTPB_MILLER, 0, s>>>(m, a, flags, c->f + o, c->rst + o, c->sl + 4 * o, hi, lo, k == 0, k == S - 1);
@@ -273,10 +316,14 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
     } else if (norm) k_miller_norm<<<nblk(m, ZKV_HTPB_MILLER), ZKV_HTPB_MILLER, 0, s>>>(m, a, flags, c->f + o);
     else k_miller<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, a, flags, c->f + o);
     if (timed) CK(cudaEventRecord(c->ev[4], s));
-    if (g_final_exp_stages && !timed && c->fes && c->fes_cap >= o + (size_t)m) {
+    if (vk->tune.layout.load()) {
+        if (stages && !timed) { for (int st = 0; st < 4; st++) k_final_exp_lz<<<nblk(m, LZ_NT), LZ_NT, LZ_SMEM_BYTES, s>>>(m, st, st, c->f + o, c->fes + 6 * o, flags, j.d_status + jo); nl += 3; }
+        else k_final_exp_lz<<<nblk(m, LZ_NT), LZ_NT, LZ_SMEM_BYTES, s>>>(m, 0, 3, c->f + o, c->fes + 6 * o, flags, j.d_status + jo);
+    } else if (stages && !timed) {
         for (int st = 0; st < 4; st++) k_final_exp_stage<<<nblk(m, ZKV_HTPB_FE), ZKV_HTPB_FE, 0, s>>>(m, st, c->f + o, c->fes + 5 * o, flags, j.d_status + jo);
         nl += 3;
     } else k_final_exp<<<nblk(m, ZKV_HTPB_FE), ZKV_HTPB_FE, 0, s>>>(m, c->f + o, flags, j.d_status + jo, nullptr, 0);
+    DBG("final exponentiation");
     if (timed) CK(cudaEventRecord(c->ev[5], s));
     g_launches += nl + 2;                   // + Miller loop (first or only kernel) + final exponentiation (first or only kernel)
     CK(cudaGetLastError());
@@ -302,8 +349,10 @@ static int fork_join(DevCtx* c, cudaStream_t main, size_t n, int chunks, F fn) {
 static int run_verify(DevCtx* c, const Job& j) {
     if (j.n == 0) return 0;
     int ns = (j.mode == SIG_GENERIC) ? j.k : 2;
-    int rc = ctx_reserve(c, j.n, (size_t)ns * 8); if (rc) return rc;
-    int chunks = g_overlap_chunks;
+    int rc = ctx_acquire(c, c->stream); if (rc) return rc;
+    if (c->busy && (j.n > c->cap || j.n > c->fes_cap || j.n * (size_t)ns * 8 > c->scal_words)) { CK(cudaEventSynchronize(c->ev_busy)); c->busy = false; }   // growing frees buffers an earlier asynchronous call may still use
+    rc = ctx_reserve(c, j.n, (size_t)ns * 8); if (rc) return rc;
+    int chunks = j.vk->tune.overlap_chunks.load();
     if (j.n < (size_t)8192 || chunks <= 1) return enqueue_chain(c, j, 0, 0, (int)j.n, c->stream, true);
     return fork_join(c, c->stream, j.n, chunks, [&](size_t o, int m, cudaStream_t s) { return enqueue_chain(c, j, o, o, m, s, false); });
 }
@@ -315,9 +364,11 @@ static void collect_stage_ms(DevCtx* c);
 // job(first, count, d_block) describes the chunk, with pointers into its device input block and d_status = c->d_out + first.
 // in_bytes: upper bound of the whole batch's input.  On return c->h_out[0..m) holds the status bytes.
 template <class Pack, class MakeJob>
-static int host_pipeline(DevCtx* c, size_t m, size_t in_bytes, int ns, Pack pack, MakeJob job) {
+static int host_pipeline(DevCtx* c, const zkv_vk* vk, size_t m, size_t in_bytes, int ns, Pack pack, MakeJob job) {
+    if (c->busy) { CK(cudaEventSynchronize(c->ev_busy)); c->busy = false; }      // a host call blocks anyway: wait out an earlier asynchronous device call here
     int rc = ctx_reserve(c, m, (size_t)ns * 8); if (rc) return rc;
-    int chunks = (m < (size_t)8192 || g_overlap_chunks <= 1) ? 1 : g_overlap_chunks;
+    const int oc = vk->tune.overlap_chunks.load();
+    int chunks = (m < (size_t)8192 || oc <= 1) ? 1 : oc;
     rc = ctx_stage(c, in_bytes + 256 * (size_t)chunks, m); if (rc) return rc;
     size_t per = (m + chunks - 1) / chunks;
     per = (per + ZKV_HTPB - 1) / ZKV_HTPB * ZKV_HTPB;
@@ -376,7 +427,7 @@ extern "C" int zkv_groth16_verify_batch(const zkv_vk* vk, const uint8_t* proofs,
     return for_each_device(vk, n, [&](DevCtx* c, size_t b, size_t e) -> int {
         for (size_t s0 = b; s0 < e; s0 += MAX_CHUNK) {
             size_t m = std::min(MAX_CHUNK, e - s0);
-            int rc = host_pipeline(c, m, m * (256 + (size_t)k * 32), k,
+            int rc = host_pipeline(c, vk, m, m * (256 + (size_t)k * 32), k,
                 [&](size_t first, size_t cnt, uint8_t* dst) -> size_t {
                     memcpy(dst, proofs + (s0 + first) * 256, cnt * 256); memcpy(dst + cnt * 256, signals + (s0 + first) * (size_t)k * 32, cnt * (size_t)k * 32);
                     return cnt * (256 + (size_t)k * 32);
@@ -446,6 +497,7 @@ extern "C" int zkv_risc0_initialize(zkv_risc0* h, const uint8_t control_root[32]
     {
         std::lock_guard<std::mutex> lk(c->mu);
         CK(cudaSetDevice(c->device));
+        if (c->busy) { CK(cudaEventSynchronize(c->ev_busy)); c->busy = false; }
         int rc = ctx_reserve(c, 1, 24); if (rc) return rc;
         uint32_t sc[24]; memset(sc, 0, sizeof sc);
         uint8_t w32[32];
@@ -480,6 +532,7 @@ extern "C" int zkv_risc0_get_verifier_key_digest(const zkv_risc0* h, uint8_t out
 
 // Host-side front checks shared by RISC Zero and SP1 (risc0/verifier.rs:151-170, sp1/verifier.rs:64-83):
 // returns the indices that reach the Groth16 stage; everything else gets its final status here.
+static bool offsets_ok(const uint64_t* off, size_t n) { for (size_t i = 0; i < n; i++) if (off[i + 1] < off[i]) return false; return true; }
 static void front_filter(const uint8_t* blobs, const uint64_t* off, size_t n, const uint8_t selector[4], uint8_t* status_out, std::vector<uint32_t>& cand) {
     cand.clear(); cand.reserve(n);
     for (size_t i = 0; i < n; i++) {
@@ -495,6 +548,7 @@ static int risc0_batch(const zkv_risc0* h, const uint8_t* seals, const uint64_t*
     if (!h || (n && (!seals || !seal_off || !a32 || (!integrity && !b32) || !status_out))) return fail(ZKV_ERR_ARG, "zkv_risc0_verify_batch: null argument");
     if (n == 0) return 0;
     if (n > 0xffffffffull) return fail(ZKV_ERR_ARG, "batch too large");
+    if (!offsets_ok(seal_off, n)) return fail(ZKV_ERR_ARG, "seal offsets must be non-decreasing");
     if (!h->initialized) { memset(status_out, ZKV_INVALID_INITIALIZATION, n); return 0; }     // risc0/verifier.rs:84-86, 99-101
     std::vector<uint32_t> cand; front_filter(seals, seal_off, n, h->selector, status_out, cand);
     const zkv_vk* vk = h->vk;
@@ -502,7 +556,7 @@ static int risc0_batch(const zkv_risc0* h, const uint8_t* seals, const uint64_t*
         for (size_t s0 = b; s0 < e; s0 += MAX_CHUNK) {
             size_t m = std::min(MAX_CHUNK, e - s0);
             const size_t per = integrity ? 32 : 64;
-            int rc = host_pipeline(c, m, m * (256 + per), 2,
+            int rc = host_pipeline(c, vk, m, m * (256 + per), 2,
                 [&](size_t first, size_t cnt, uint8_t* dst) -> size_t {
                     uint8_t* pa = dst + cnt * 256; uint8_t* pb = pa + cnt * 32;
                     for (size_t t = 0; t < cnt; t++) {
@@ -545,14 +599,15 @@ extern "C" int zkv_risc0_verify_batch_device(const zkv_risc0* h, int device, con
     if (!c) return fail(ZKV_ERR_ARG, "device not in the handle's device list");
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(device));
-    if (!h->initialized) { CK(cudaMemsetAsync(d_status_out, ZKV_INVALID_INITIALIZATION, n, (cudaStream_t)stream)); return 0; }
     if (n > MAX_CHUNK * 8) return fail(ZKV_ERR_ARG, "device batch too large");
+    if (!h->initialized) { CK(cudaMemsetAsync(d_status_out, ZKV_INVALID_INITIALIZATION, n, (cudaStream_t)stream)); return 0; }
     Job j; memset(&j, 0, sizeof j);
     j.vk = h->vk; j.n = n; j.recs = (const uint8_t*)d_seals260; j.stride = 260; j.off = 4; j.check_selector = 1; j.selector_le = sel_le(h->selector);
     j.mode = SIG_RISC0_VERIFY; j.sig_a = (const uint8_t*)d_image_ids; j.sig_b = (const uint8_t*)d_journal_digests; j.hc = h->hc; j.base = h->base; j.all_fail = h->all_fail;
     j.d_status = (uint8_t*)d_status_out;
-    cudaStream_t keep = c->stream; if (stream) c->stream = (cudaStream_t)stream;
+    cudaStream_t keep = c->stream; c->stream = (cudaStream_t)stream;          // NULL is the legacy default stream, as for any CUDA call
     int rc = run_verify(c, j);
+    if (!rc) rc = ctx_release_async(c, c->stream);
     c->stream = keep;
     return rc;
 }
@@ -575,6 +630,7 @@ extern "C" int zkv_sp1_verify_batch(const zkv_sp1* h, const uint8_t* vkeys, cons
     if (!h || (n && (!vkeys || !public_values || !pv_off || !proofs || !proof_off || !status_out))) return fail(ZKV_ERR_ARG, "zkv_sp1_verify_batch: null argument");
     if (n == 0) return 0;
     if (n > 0xffffffffull) return fail(ZKV_ERR_ARG, "batch too large");
+    if (!offsets_ok(proof_off, n) || !offsets_ok(pv_off, n)) return fail(ZKV_ERR_ARG, "proof / public-value offsets must be non-decreasing");
     std::vector<uint32_t> cand; front_filter(proofs, proof_off, n, h->verifier_hash, status_out, cand);
     const zkv_vk* vk = h->vk;
     return for_each_device(vk, cand.size(), [&](DevCtx* c, size_t b, size_t e) -> int {
@@ -582,7 +638,7 @@ extern "C" int zkv_sp1_verify_batch(const zkv_sp1* h, const uint8_t* vkeys, cons
             size_t m = std::min(MAX_CHUNK, e - s0);
             size_t pvb = 0; for (size_t t = 0; t < m; t++) { size_t i = cand[s0 + t]; pvb += pv_off[i + 1] - pv_off[i]; }
             // chunk block layout: [proofs cnt x 256][vkeys cnt x 32][offsets (cnt + 1) x 8][public values]
-            int rc = host_pipeline(c, m, m * (256 + 32 + 8) + 8 * 64 + pvb, 2,
+            int rc = host_pipeline(c, vk, m, m * (256 + 32 + 8) + 8 * 64 + pvb, 2,
                 [&](size_t first, size_t cnt, uint8_t* dst) -> size_t {
                     uint8_t* pk = dst + cnt * 256; uint64_t* po = (uint64_t*)(pk + cnt * 32); uint8_t* pp = (uint8_t*)(po + cnt + 1);
                     uint64_t acc = 0;
@@ -621,8 +677,9 @@ extern "C" int zkv_sp1_verify_batch_device(const zkv_sp1* h, int device, const v
     j.vk = h->vk; j.n = n; j.recs = (const uint8_t*)d_proofs260; j.stride = 260; j.off = 4; j.check_selector = 1; j.selector_le = sel_le(h->verifier_hash);
     j.mode = SIG_SP1; j.sig_a = (const uint8_t*)d_vkeys; j.sig_b = (const uint8_t*)d_public_values; j.pv_off = nullptr; j.pv_stride = pv_stride; j.base = c->h_ic0;
     j.d_status = (uint8_t*)d_status_out;
-    cudaStream_t keep = c->stream; if (stream) c->stream = (cudaStream_t)stream;
+    cudaStream_t keep = c->stream; c->stream = (cudaStream_t)stream;
     int rc = run_verify(c, j);
+    if (!rc) rc = ctx_release_async(c, c->stream);
     c->stream = keep;
     return rc;
 }
@@ -652,14 +709,16 @@ static int pairing4_chain(DevCtx* c, const zkv_vk* vk, size_t o, int n, const ui
 }
 static int run_pairing4(DevCtx* c, const zkv_vk* vk, size_t n_, const uint8_t* d_g1s, const uint8_t* d_g2s, uint8_t* d_ok, uint8_t* d_gt, uint8_t* d_miller) {
     if (n_ == 0) return 0;
-    int rc = ctx_reserve(c, n_, 8); if (rc) return rc;
+    int rc = ctx_acquire(c, c->stream); if (rc) return rc;
+    if (c->busy && (n_ > c->cap || n_ > c->fes_cap)) { CK(cudaEventSynchronize(c->ev_busy)); c->busy = false; }
+    rc = ctx_reserve(c, n_, 8); if (rc) return rc;
     cudaStream_t s = c->stream;
     if (!vk->valid) {   // a fixed G2 point is invalid: every call reverts
         CK(cudaMemsetAsync(d_ok, 2, n_, s)); if (d_gt) CK(cudaMemsetAsync(d_gt, 0, n_ * 384, s)); if (d_miller) CK(cudaMemsetAsync(d_miller, 0, n_ * 384, s));
         for (int e = 0; e < 6; e++) CK(cudaEventRecord(c->ev[e], s));
         return 0;
     }
-    int chunks = g_overlap_chunks;
+    int chunks = vk->tune.overlap_chunks.load();
     if (n_ < (size_t)8192 || chunks <= 1) return pairing4_chain(c, vk, 0, (int)n_, d_g1s, d_g2s, d_ok, d_gt, d_miller, s, true);
     return fork_join(c, s, n_, chunks, [&](size_t o, int m, cudaStream_t st) { return pairing4_chain(c, vk, o, m, d_g1s, d_g2s, d_ok, d_gt, d_miller, st, false); });
 }
@@ -671,6 +730,7 @@ extern "C" int zkv_pairing4_batch(const zkv_vk* vk, const uint8_t* g1s, const ui
         for (size_t s0 = b; s0 < e; s0 += CH) {
             size_t m = std::min(CH, e - s0);
             size_t ob = m + (gt_out ? m * 384 : 0) + (miller_out ? m * 384 : 0);
+            if (c->busy) { CK(cudaEventSynchronize(c->ev_busy)); c->busy = false; }
             int rc = ctx_stage(c, m * 384, ob); if (rc) return rc;
             memcpy(c->h_pin, g1s + s0 * 256, m * 256); memcpy(c->h_pin + m * 256, g2s + s0 * 128, m * 128);
             CK(cudaMemcpyAsync(c->d_in, c->h_pin, m * 384, cudaMemcpyHostToDevice, c->stream));
@@ -690,10 +750,12 @@ extern "C" int zkv_pairing4_batch_device(const zkv_vk* vk, int device, const voi
     if (!vk || !d_g1s || !d_g2s || !d_ok_out) return fail(ZKV_ERR_ARG, "zkv_pairing4_batch_device: null argument");
     DevCtx* c = vk_ctx(vk, device);
     if (!c) return fail(ZKV_ERR_ARG, "device not in the key's device list");
+    if (n > MAX_CHUNK * 8) return fail(ZKV_ERR_ARG, "device batch too large");
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(device));
-    cudaStream_t keep = c->stream; if (stream) c->stream = (cudaStream_t)stream;
+    cudaStream_t keep = c->stream; c->stream = (cudaStream_t)stream;
     int rc = run_pairing4(c, vk, n, (const uint8_t*)d_g1s, (const uint8_t*)d_g2s, (uint8_t*)d_ok_out, (uint8_t*)d_gt_out, nullptr);
+    if (!rc) rc = ctx_release_async(c, c->stream);
     c->stream = keep;
     return rc;
 }
@@ -702,9 +764,11 @@ extern "C" int zkv_pairing4_batch_device(const zkv_vk* vk, int device, const voi
 extern "C" int zkv_vk_x_batch(const zkv_vk* vk, const uint8_t* signals, int k, size_t n, uint8_t* out_points) {
     if (!vk || !signals || !out_points || k + 1 != vk->n_ic) return fail(ZKV_ERR_ARG, "zkv_vk_x_batch: bad argument");
     if (n == 0) return 0;
+    if (n > MAX_CHUNK * 8) return fail(ZKV_ERR_ARG, "zkv_vk_x_batch: batch too large");
     DevCtx* c = vk->devs[0];
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
+    if (c->busy) { CK(cudaEventSynchronize(c->ev_busy)); c->busy = false; }
     int rc = ctx_reserve(c, n, (size_t)k * 8); if (rc) return rc;
     rc = ctx_stage(c, n * (size_t)k * 32, n * 64); if (rc) return rc;
     CK(cudaMemcpyAsync(c->d_in, signals, n * (size_t)k * 32, cudaMemcpyHostToDevice, c->stream));
@@ -740,11 +804,26 @@ extern "C" int zkv_fp_mul_batch(const uint8_t* a, const uint8_t* b, size_t n, ui
     return with_scratch(device, a, n * 32, b, n * 32, out, n * 32, &dummy, 0, [&](uint8_t* d0, uint8_t* d1, uint8_t* o0, uint8_t*) { k_fp_mul_bytes<<<nblk(n), TPB>>>((int)n, d0, d1, o0); });
 }
 extern "C" int zkv_fp12_op_batch(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out, int device) {
-    if (!a || !out || op < 0 || op > 9 || ((op == 0 || op == 2 || op == 9) && !b)) return fail(ZKV_ERR_ARG, "zkv_fp12_op_batch: bad argument");
+    const bool slots = op >= 16;                    // 16 + k: the shared-memory-resident form (lazy.cuh) of operation k
+    const int k = slots ? op - 16 : op;
+    if (!a || !out || k < 0 || k > (slots ? 10 : 9) || ((k == 0 || k == 2 || k == 9 || k == 10) && !b)) return fail(ZKV_ERR_ARG, "zkv_fp12_op_batch: bad argument");
     if (n == 0) return 0;
     uint8_t dummy;
-    return with_scratch(device, a, n * 384, b ? b : &dummy, b ? n * 384 : 0, out, n * 384, &dummy, 0,
-                        [&](uint8_t* d0, uint8_t* d1, uint8_t* o0, uint8_t*) { k_fp12_op<<<nblk(n, ZKV_HTPB), ZKV_HTPB>>>((int)n, op, d0, b ? d1 : nullptr, o0); });
+    if (!slots)
+        return with_scratch(device, a, n * 384, b ? b : &dummy, b ? n * 384 : 0, out, n * 384, &dummy, 0,
+                            [&](uint8_t* d0, uint8_t* d1, uint8_t* o0, uint8_t*) { k_fp12_op<<<nblk(n, ZKV_HTPB), ZKV_HTPB>>>((int)n, k, d0, b ? d1 : nullptr, o0); });
+    const size_t launched = (size_t)nblk(n, LZ_NT) * LZ_NT;
+    std::vector<uint8_t> sink(1);
+    // second output buffer of with_scratch doubles as the kernel's per-thread scratch (7 Fp12 per launched thread); nothing is copied back from it
+    if (zkv_device_count() <= device || device < 0) return fail(ZKV_ERR_CUDA, "no such CUDA device (this library has no CPU path)");
+    CK(cudaSetDevice(device));
+    CK(cudaFuncSetAttribute(k_lz_fp12_op, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_BYTES));
+    fp12* scratch = nullptr; CK(cudaMalloc(&scratch, launched * 7 * sizeof(fp12)));
+    nline_t* ztab = nullptr; CK(cudaMalloc(&ztab, ZKV_LINES_PER_G2 * sizeof(nline_t))); CK(cudaMemset(ztab, 0, ZKV_LINES_PER_G2 * sizeof(nline_t)));
+    int rc = with_scratch(device, a, n * 384, b ? b : &dummy, b ? n * 384 : 0, out, n * 384, &dummy, 0,
+                          [&](uint8_t* d0, uint8_t* d1, uint8_t* o0, uint8_t*) { k_lz_fp12_op<<<nblk(n, LZ_NT), LZ_NT, LZ_SMEM_BYTES>>>((int)n, k, d0, b ? d1 : nullptr, o0, scratch, ztab); });
+    cudaFree(scratch); cudaFree(ztab);
+    return rc;
 }
 extern "C" int zkv_g2_check_batch(const uint8_t* g2s, size_t n, uint8_t* out, int device) {
     if (!g2s || !out) return fail(ZKV_ERR_ARG, "null");
@@ -790,10 +869,16 @@ extern "C" long long zkv_wave_proofs(int device, int kernel) {
     if (cudaSetDevice(device) != cudaSuccess) return fail(ZKV_ERR_CUDA, "cudaSetDevice failed");
     cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(ZKV_ERR_CUDA, "cudaGetDeviceProperties failed");
     int per_sm = 0;
-    cudaError_t e = kernel == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_miller_norm, ZKV_HTPB_MILLER, 0)
-                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_final_exp, ZKV_HTPB_FE, 0);
+    cudaError_t e; int tpb;
+    switch (kernel) {
+        case 0: tpb = LZ_NT; cudaFuncSetAttribute(k_miller_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_BYTES); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_miller_lz, LZ_NT, LZ_SMEM_BYTES); break;
+        case 1: tpb = LZ_NT; cudaFuncSetAttribute(k_final_exp_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_BYTES); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_final_exp_lz, LZ_NT, LZ_SMEM_BYTES); break;
+        case 2: tpb = ZKV_HTPB_MILLER; e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_miller_norm, ZKV_HTPB_MILLER, 0); break;
+        case 3: tpb = ZKV_HTPB_FE; e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_final_exp, ZKV_HTPB_FE, 0); break;
+        default: return fail(ZKV_ERR_ARG, "zkv_wave_proofs: kernel");
+    }
     if (e != cudaSuccess) return fail(ZKV_ERR_CUDA, cudaGetErrorString(e));
-    return (long long)prop.multiProcessorCount * per_sm * (kernel == 0 ? ZKV_HTPB_MILLER : ZKV_HTPB_FE);
+    return (long long)prop.multiProcessorCount * per_sm * tpb;
 }
 extern "C" int zkv_imad_peak(int device, double* wide_per_s, double* fpmul_per_s) {
     if (zkv_device_count() <= device || device < 0) return fail(ZKV_ERR_CUDA, "no such CUDA device");

@@ -32,6 +32,30 @@ def _dev_array(devices):
     return arr, len(devices)
 
 
+def _tune(handle_vk, option, value):
+    """zkv_vk_tune on a key handle: returns the previous value; value=None only reads the setting (include/zkv.h lists the options)."""
+    r = N.lib().zkv_vk_tune(handle_vk, N.TUNE[option], N.ZKV_TUNE_QUERY if value is None else int(value))
+    if r < 0:
+        N.check(r)
+    return r
+
+
+def _need32(**kw):
+    """the reference takes typed B256 / FixedBytes<32> values (risc0/verifier.rs:78-104, sp1/verifier.rs:39-46): anything else is a caller bug"""
+    for name, v in kw.items():
+        if len(v) != 32:
+            raise ValueError("%s must be exactly 32 bytes, got %d" % (name, len(v)))
+
+
+def _need32_each(n, **kw):
+    for name, seq in kw.items():
+        if len(seq) != n:
+            raise ValueError("%s: expected %d entries, got %d" % (name, n, len(seq)))
+        for v in seq:
+            if len(v) != 32:
+                raise ValueError("every element of %s must be exactly 32 bytes" % name)
+
+
 class VerificationKey:
     """common/types.rs:17-23.  Points as EVM words: alpha 64 B, beta/gamma/delta 128 B each in wire order
     x[0],x[1],y[0],y[1]; ic = list of 64-byte points."""
@@ -70,6 +94,10 @@ class VerificationKey:
         out = (C.c_float * 5)()
         n = N.lib().zkv_last_stage_ms(self._h, device, out, 5)
         return dict(zip(("decode_hash", "vk_x", "g2_check", "miller", "final_exp"), list(out)[:max(n, 0)]))
+
+    def tune(self, option, value=None):
+        """Per-key tuning (overlap, normalised_lines, miller_segments, final_exp_stages, layout); returns the previous value."""
+        return _tune(self._h, option, value)
 
 
 class Groth16Verifier:
@@ -111,18 +139,24 @@ class RiscZeroVerifier:
             pass
 
     # -- IRiscZeroVerifier
+    def tune(self, option, value=None):
+        return _tune(N.lib().zkv_risc0_vk(self._h), option, value)
+
     def initialize(self, control_root, bn254_control_id):
+        _need32(control_root=control_root, bn254_control_id=bn254_control_id)
         rc = N.lib().zkv_risc0_initialize(self._h, control_root, bn254_control_id)
         if rc == N.ZKV_ERR_STATE:
             raise E.AlreadyInitialized()
         N.check(rc)
 
     def verify(self, seal, image_id, journal_digest):
+        _need32(image_id=image_id, journal_digest=journal_digest)
         st = C.c_uint8(0)
         N.check(N.lib().zkv_risc0_verify(self._h, seal, len(seal), image_id, journal_digest, C.byref(st)))
         return self._result(st.value, seal)
 
     def verify_integrity(self, receipt_seal, claim_digest):
+        _need32(claim_digest=claim_digest)
         st = C.c_uint8(0)
         N.check(N.lib().zkv_risc0_verify_integrity(self._h, receipt_seal, len(receipt_seal), claim_digest, C.byref(st)))
         return self._result(st.value, receipt_seal)
@@ -146,6 +180,7 @@ class RiscZeroVerifier:
     # -- batch variants
     def verify_batch(self, seals, image_ids, journal_digests):
         n = len(seals)
+        _need32_each(n, image_ids=image_ids, journal_digests=journal_digests)
         st = np.zeros(n, dtype=np.uint8)
         off = _offsets(seals)
         N.check(N.lib().zkv_risc0_verify_batch(self._h, b"".join(seals) or b"\0", off.ctypes.data, b"".join(image_ids) or b"\0",
@@ -154,6 +189,7 @@ class RiscZeroVerifier:
 
     def verify_integrity_batch(self, seals, claim_digests):
         n = len(seals)
+        _need32_each(n, claim_digests=claim_digests)
         st = np.zeros(n, dtype=np.uint8)
         off = _offsets(seals)
         N.check(N.lib().zkv_risc0_verify_integrity_batch(self._h, b"".join(seals) or b"\0", off.ctypes.data, b"".join(claim_digests) or b"\0", n, st.ctypes.data))
@@ -205,7 +241,11 @@ class Sp1Verifier:
         except Exception:
             pass
 
+    def tune(self, option, value=None):
+        return _tune(N.lib().zkv_sp1_vk(self._h), option, value)
+
     def verify_proof(self, program_vkey, public_values, proof_bytes):
+        _need32(program_vkey=program_vkey)
         st = C.c_uint8(0)
         N.check(N.lib().zkv_sp1_verify_proof(self._h, program_vkey, public_values or b"\0", len(public_values), proof_bytes or b"\0", len(proof_bytes), C.byref(st)))
         if st.value == N.ZKV_OK:
@@ -224,6 +264,9 @@ class Sp1Verifier:
 
     def verify_batch(self, program_vkeys, public_values, proofs):
         n = len(proofs)
+        _need32_each(n, program_vkeys=program_vkeys)
+        if len(public_values) != n:
+            raise ValueError("public_values: expected %d entries, got %d" % (n, len(public_values)))
         st = np.zeros(n, dtype=np.uint8)
         po, vo = _offsets(proofs), _offsets(public_values)
         N.check(N.lib().zkv_sp1_verify_batch(self._h, b"".join(program_vkeys) or b"\0", b"".join(public_values) or b"\0", vo.ctypes.data,
@@ -296,13 +339,9 @@ def g2_check_batch(g2s, n, device=0):
     return out
 
 
-def set_overlap(chunks):
-    """Chunks a device batch is cut into for stream overlap (1 = serial chain with per-stage timing); returns the previous value."""
-    return N.lib().zkv_set_overlap(int(chunks))
-
-
 def wave_proofs(device, kernel):
-    """Proofs in one full wave of the verification Miller-loop kernel (kernel 0) or the final exponentiation (kernel 1) on `device`."""
+    """Proofs in one full wave of the verification Miller-loop kernel (kernel 0) or the final exponentiation (kernel 1) on `device`;
+    2 / 3 = the same for the round-1 layout."""
     w = int(N.lib().zkv_wave_proofs(int(device), int(kernel)))
     if w <= 0:
         N.check(w if w < 0 else N.ZKV_ERR_CUDA)
@@ -312,21 +351,6 @@ def wave_proofs(device, kernel):
 def launch_count():
     """Kernels launched by the verification chains since the library was loaded."""
     return int(N.lib().zkv_launch_count())
-
-
-def set_final_exp_stages(on):
-    """Verification path: staged final exponentiation for chunked batches on (default) or off; returns the previous setting."""
-    return N.lib().zkv_set_final_exp_stages(int(on))
-
-
-def set_miller_segments(segments):
-    """Verification path: Miller loop as `segments` kernels per chunk (1 = one kernel); returns the previous value."""
-    return N.lib().zkv_set_miller_segments(int(segments))
-
-
-def set_normalised_lines(on):
-    """Verification path: normalised gamma / delta line tables on (default) or off; returns the previous setting."""
-    return N.lib().zkv_set_normalised_lines(int(on))
 
 
 def imad_peak(device=0):

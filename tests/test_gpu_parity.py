@@ -267,14 +267,17 @@ def test_normalised_and_unscaled_lines_agree(Z, gpu, fx):
     S.mutate_risc0(batch, gpu, S.SplitMix64(0xB200000A))
     ro = O.Risc0Oracle(oracle_vk(vk)); ro.initialize(fx["control_root"], fx["bn254_control_id"])
     want = ro.verify_batch(batch.seals, batch.image_ids, batch.journals)
-    prev = Z.set_normalised_lines(1)
-    try:
-        a = v.verify_batch(batch.seals, batch.image_ids, batch.journals)
-        Z.set_normalised_lines(0)
-        b = v.verify_batch(batch.seals, batch.image_ids, batch.journals)
-    finally:
-        Z.set_normalised_lines(prev)
-    assert a.tolist() == want.tolist() and b.tolist() == want.tolist()
+    assert v.tune("normalised_lines") == 1 and v.tune("layout") == 1          # the defaults; tuning is per key, not process-wide
+    a = v.verify_batch(batch.seals, batch.image_ids, batch.journals)          # shared-memory kernels, normalised lines
+    v.tune("layout", 0)
+    a0 = v.verify_batch(batch.seals, batch.image_ids, batch.journals)         # round-1 kernels, normalised lines
+    v.tune("normalised_lines", 0)
+    b = v.verify_batch(batch.seals, batch.image_ids, batch.journals)          # round-1 kernels, unscaled lines (the pairing service's loop)
+    v.tune("layout", 1)
+    b1 = v.verify_batch(batch.seals, batch.image_ids, batch.journals)         # unscaled lines + shared-memory final exponentiation
+    assert a.tolist() == want.tolist() and b.tolist() == want.tolist() and a0.tolist() == want.tolist() and b1.tolist() == want.tolist()
+    other = Z.RiscZeroVerifier(Z.VerificationKey(0, vk.alpha, vk.beta, vk.gamma, vk.delta, vk.ic))
+    assert other.tune("normalised_lines") == 1                                # another key handle keeps its own settings
     assert 0 < int((want == 0).sum()) < n
 
 
@@ -441,31 +444,28 @@ def test_segmented_miller_loop_matches(Z, gpu, fx):
     ro = O.Risc0Oracle(oracle_vk(vk)); ro.initialize(fx["control_root"], fx["bn254_control_id"])
     sub = 600
     want = ro.verify_batch(batch.seals[:sub], batch.image_ids[:sub], batch.journals[:sub])
-    prev = Z.set_miller_segments(1)
-    try:
+    for layout in (1, 0):                                  # shared-memory kernels (default), round-1 kernels
+        v.tune("layout", layout)
+        v.tune("miller_segments", 1)
         base = v.verify_batch(batch.seals, batch.image_ids, batch.journals)
-        assert base[:sub].tolist() == want.tolist()
+        assert base[:sub].tolist() == want.tolist(), layout
         for segs in (2, 4, 7):
-            Z.set_miller_segments(segs)
-            assert v.verify_batch(batch.seals, batch.image_ids, batch.journals).tolist() == base.tolist(), segs
+            v.tune("miller_segments", segs)
+            assert v.verify_batch(batch.seals, batch.image_ids, batch.journals).tolist() == base.tolist(), (layout, segs)
         for fe in (0, 1):                                  # one-kernel / staged final exponentiation
-            prev_fe = Z.set_final_exp_stages(fe)
-            try:
-                assert v.verify_batch(batch.seals, batch.image_ids, batch.journals).tolist() == base.tolist(), ("fe", fe)
-            finally:
-                Z.set_final_exp_stages(prev_fe)
-    finally:
-        Z.set_miller_segments(prev)
+            v.tune("final_exp_stages", fe)
+            assert v.verify_batch(batch.seals, batch.image_ids, batch.journals).tolist() == base.tolist(), (layout, "fe", fe)
 
 
 @pytest.mark.gpu
 def test_launch_counter_and_wave_size(Z, gpu, fx):
     """zkv_launch_count counts every kernel of the verification chains (bench.py's gpu_launches); zkv_wave_proofs is SMs x resident blocks
-    x 128 threads for the Miller (three blocks per SM) and final-exponentiation (two) kernels."""
+    x 128 threads: two blocks per SM for the shared-memory Miller / final-exponentiation kernels, three / two for the round-1 kernels."""
     import torch
     from stylus_zkvm_verifiers_b200 import synth as S
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    assert Z.wave_proofs(0, 0) == sms * 3 * 128 and Z.wave_proofs(0, 1) == sms * 2 * 128
+    assert Z.wave_proofs(0, 0) == sms * 2 * 128 and Z.wave_proofs(0, 1) == sms * 2 * 128
+    assert Z.wave_proofs(0, 2) == sms * 3 * 128 and Z.wave_proofs(0, 3) == sms * 2 * 128
     vk = S.make_vk(gpu, 0, 6, 0xB200000D)
     kv = Z.VerificationKey(0, vk.alpha, vk.beta, vk.gamma, vk.delta, vk.ic)
     v = Z.RiscZeroVerifier(kv); v.initialize(fx["control_root"], fx["bn254_control_id"])
@@ -475,7 +475,7 @@ def test_launch_counter_and_wave_size(Z, gpu, fx):
     assert Z.launch_count() - c0 == 6                      # one serial chain: decode, signals, vk_x, G2 check, Miller loop, final exponentiation
     n = 8192 + 300
     big = S.make_risc0_batch(gpu, vk, v.get_selector(), fx["control_root"], fx["bn254_control_id"], fx["sys0"], n, 0xB200000E, pool=8)
-    chunks, segs, fe = Z.set_overlap(0), Z.set_miller_segments(0), Z.set_final_exp_stages(-1)     # out-of-range arguments read the settings
+    chunks, segs, fe = v.tune("overlap"), v.tune("miller_segments"), v.tune("final_exp_stages")
     c0 = Z.launch_count()
     assert set(v.verify_batch(big.seals, big.image_ids, big.journals).tolist()) == {0}
     per_chain = 4 + segs + (4 if fe else 1)

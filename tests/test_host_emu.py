@@ -22,7 +22,7 @@ G1 = w32(1) + w32(2)
 def emu():
     d = os.path.join(ROOT, "tests", "host_emu")
     so = os.path.join(d, "libzkv_emu.so")
-    srcs = [os.path.join(d, "emu.cpp")] + [os.path.join(ROOT, "stylus_zkvm_verifiers_b200", "csrc", f) for f in ("bn254.cuh", "bn254_consts.cuh")]
+    srcs = [os.path.join(d, "emu.cpp"), os.path.join(d, "lazy_leaf_host.h")] + [os.path.join(ROOT, "stylus_zkvm_verifiers_b200", "csrc", f) for f in ("bn254.cuh", "bn254_consts.cuh", "lazy.cuh", "lazy_gen.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, srcs[0]])
     return C.CDLL(so)
@@ -117,6 +117,50 @@ def test_pairing_values_bit_exact(emu, consts):
             d2 = b"".join(g1s[64 * j:64 * j + 64] + g2s[j] for j in keep)
             r2, _, gt2 = O.ec_pairing(d2, debug=True)
             assert emu.emu_verify_norm_gt(g1s, q, fixed, mask, go) == r2[31] and go.raw == gt2, mask
+
+
+def test_lazy_generator_bounds_and_current_header():
+    """tools/gen_lazy.py proves every bound of the lazily reduced routines and checks their values; csrc/lazy_gen.cuh is what it emits."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_lazy", os.path.join(ROOT, "tools", "gen_lazy.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    assert open(os.path.join(ROOT, "stylus_zkvm_verifiers_b200", "csrc", "lazy_gen.cuh")).read() == g.render()
+
+
+def test_lazy_tower_on_slots_matches_round1_tower(emu):
+    """csrc/lazy.cuh (shared-memory slots, lazily reduced Fp6 routines) against the round-1 tower and the oracle, including all-(p-1),
+    all-zero and mixed-extreme operands; the portable leaves abort on any carry, borrow or reduction-range violation."""
+    import random
+    rnd = random.Random(5)
+
+    def rv(n, mode):
+        if mode == 0: return [P - 1] * n
+        if mode == 1: return [0] * n
+        if mode == 2: return [rnd.choice([0, P - 1, 1, P - 2]) for _ in range(n)]
+        return [rnd.randrange(P) for _ in range(n)]
+    out, ref, o12 = C.create_string_buffer(192), C.create_string_buffer(192), C.create_string_buffer(384)
+    for it in range(120):
+        m = it % 4 if it < 40 else 3
+        a = b"".join(w32(x) for x in rv(6, m)); b = b"".join(w32(x) for x in rv(6, (m + it // 4) % 4 if it < 40 else 3))
+        for sp in (0, 1):
+            emu.emu_lz_f6mul(a, b, sp, out, ref); assert out.raw == ref.raw, (it, sp)
+    for it in range(40):
+        x = b"".join(w32(v) for v in rv(12, it % 4 if it < 20 else 3))
+        emu.emu_lz_f12sqr(x, o12); assert o12.raw == O.fp12_mul(x, x), it
+
+
+def test_lazy_miller_loop_bit_exact_with_round1_loop(emu, consts):
+    """lz_miller_norm_seg (one and several segments, pairs switched off) reproduces miller_loop_norm's Fp12 value bit for bit."""
+    rng = SplitMix64(21)
+    h = bytes.fromhex
+    vkj = consts["risc0_vk"]
+    fixed = b"".join(h(vkj[n][i][j]) for n in ("beta", "gamma", "delta") for i in range(2) for j in range(2))
+    a, b = C.create_string_buffer(384), C.create_string_buffer(384)
+    for k, (mask, nseg) in enumerate(((0, 1), (0, 8), (1, 3), (2, 1), (4, 5), (7, 2))):
+        g1s = b"".join(O.g1_mul(G1, rng.fr()) for _ in range(4))
+        q = O.g2_mul(G2_GEN, rng.fr())
+        assert emu.emu_lz_miller_norm(g1s, q, fixed, mask, nseg, a, b) == 0
+        assert a.raw == b.raw, (mask, nseg)
 
 
 def test_g1_scalar_mul(emu):

@@ -364,6 +364,128 @@ def gen_fp2_sqr():
     return p
 
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Leaf primitives of the lazily reduced tower (csrc/lazy_gen.cuh, generated by tools/gen_lazy.py, composes them):
+# wide (16-limb) products, raw wide / narrow carry chains, additions of constants that are multiples of p (offsets that
+# keep a difference non-negative), conditional subtractions of multiples of p * 2^256, and a Montgomery reduction
+# without the final subtraction.  Each is an instruction list simulated against Python integers like the rest.
+def nm(c, n=N):
+    return ["%s%d" % (c, i) for i in range(n)]
+
+
+def gen_mulw():
+    p = Prog("lz_mulw", nm("a") + nm("b"), nm("w", 16))
+    out = mul_wide(p, nm("a"), nm("b"))
+    for k in range(16):
+        p.emit("mov", "w%d" % k, out[k])
+    return p
+
+
+def gen_redc_nf():
+    """r = (T + m p) / 2^256 for a 16-limb T < 4 p 2^256, WITHOUT the final subtraction: r < T / 2^256 + p < 5 p < 2^256."""
+    p = Prog("lz_redc", nm("w", 16), nm("r"))
+    T = nm("w", 16)
+    E, O = list(T[:N]), [0] * N
+    for i in range(N):
+        reduce_row(p, E, O, carry_in=(i > 0))
+        if i < N - 1:
+            X = E[1]
+            Oin = E[2:] + [0, 0]
+            E = O
+            O = Oin
+            E[0] = p.op("add.cc", E[0], X)
+    u = [p.op("add.cc", E[1], O[0])]
+    for k in range(1, 7):
+        u.append(p.op("addc.cc", E[k + 1], O[k]))
+    u.append(p.op("addc.cc", O[7], 0))
+    p.emit("assert_nc", None)
+    for k in range(N):
+        p.emit("add.cc" if k == 0 else "addc.cc", "r%d" % k, u[k], T[N + k])
+    p.emit("assert_nc", None)
+    return p
+
+
+def gen_chain(name, op, n):
+    """raw n-limb r = a op b (op in add, sub); the simulator asserts there is no carry / borrow out."""
+    p = Prog(name, nm("a", n) + nm("b", n), nm("r", n))
+    for k in range(n):
+        p.emit(("%s.cc" % op) if k == 0 else ("%sc.cc" % op), "r%d" % k, "a%d" % k, "b%d" % k)
+    p.emit("assert_nc", None)
+    return p
+
+
+def gen_addhi():
+    """r = x + c * 2^224 for a 9-limb constant c (a multiple of p: the value modulo p is unchanged)."""
+    p = Prog("lz_addhi", nm("x", 16) + nm("c", 9), nm("r", 16))
+    for k in range(7):
+        p.emit("mov", "r%d" % k, "x%d" % k)
+    for k in range(9):
+        p.emit("add.cc" if k == 0 else "addc.cc", "r%d" % (7 + k), "x%d" % (7 + k), "c%d" % k)
+    p.emit("assert_nc", None)
+    return p
+
+
+def gen_csub(name, n):
+    """the top 8 limbs of an n-limb x (n = 8 or 16) minus the 8-limb constant k if that does not borrow, else unchanged."""
+    p = Prog(name, nm("x", n) + nm("k", 8), nm("r", n))
+    lo = n - 8
+    for k in range(lo):
+        p.emit("mov", "r%d" % k, "x%d" % k)
+    s = [p.op("sub.cc" if k == 0 else "subc.cc", "x%d" % (lo + k), "k%d" % k) for k in range(8)]
+    bor = p.op("subc", 0, 0)
+    for k in range(8):
+        p.emit("selp_eqz", "r%d" % (lo + k), s[k], "x%d" % (lo + k), bor)
+    return p
+
+
+def leaf_progs():
+    return [gen_mulw(), gen_redc_nf(), gen_chain("lz_add8", "add", 8), gen_chain("lz_sub8", "sub", 8), gen_chain("lz_addw", "add", 16),
+            gen_chain("lz_subw", "sub", 16), gen_addhi(), gen_csub("lz_csubw", 16), gen_csub("lz_csub8", 8)]
+
+
+def check_leaves(iters=600):
+    rnd = random.Random(0x1A27)
+    val = lambda v: sum(x << (32 * i) for i, x in enumerate(v))
+    lim = lambda x, n: {i: (x >> (32 * i)) & MASK for i in range(n)}
+    def run(prog, **kw):
+        inp = {}
+        for c, (x, n) in kw.items():
+            inp.update({"%s%d" % (c, i): v for i, v in lim(x, n).items()})
+        return val(prog.run(inp))
+    mulw, redc, add8, sub8, addw, subw, addhi, csubw, csub8 = leaf_progs()
+    Bw = P << 256
+    for it in range(iters):
+        a, b = rnd.getrandbits(256), rnd.getrandbits(256)
+        if it < 4:
+            a, b = [(0, 0), ((1 << 256) - 1, (1 << 256) - 1), (P - 1, P - 1), (1, (1 << 256) - 1)][it]
+        assert run(mulw, a=(a, 8), b=(b, 8)) == a * b
+        t = rnd.randrange(4 * Bw) if it > 3 else [0, 4 * Bw - 1, Bw, Bw - 1][it]
+        r = run(redc, w=(t, 16))
+        assert r < (t >> 256) + P + 1 and (r << 256) % P == t % P, "redc"
+        x, y = sorted((rnd.getrandbits(255), rnd.getrandbits(255)))
+        assert run(add8, a=(x, 8), b=(y, 8)) == x + y and run(sub8, a=(y, 8), b=(x, 8)) == y - x
+        x, y = sorted((rnd.getrandbits(511), rnd.getrandbits(511)))
+        assert run(addw, a=(x, 16), b=(y, 16)) == x + y and run(subw, a=(y, 16), b=(x, 16)) == y - x
+        c = rnd.randrange(1 << 32) * P
+        assert run(addhi, x=(x, 16), c=(c, 9)) == x + (c << 224)
+        k = rnd.randrange(1, 5)
+        w = rnd.randrange(1 << 512) if it > 3 else [k * Bw, k * Bw - 1, 0, (1 << 512) - 1][it]
+        assert run(csubw, x=(w, 16), k=(k * P, 8)) == (w - k * Bw if w >= k * Bw else w)
+        w = rnd.getrandbits(256) if it > 3 else [k * P, k * P - 1, 0, (1 << 256) - 1][it]
+        assert run(csub8, x=(w, 8), k=(k * P, 8)) == (w - k * P if w >= k * P else w)
+    return True
+
+
+LEAF_SIGS = {
+    "lz_mulw": "uint32_t* w, const uint32_t* a, const uint32_t* b", "lz_redc": "uint32_t* r, const uint32_t* w",
+    "lz_add8": "uint32_t* r, const uint32_t* a, const uint32_t* b", "lz_sub8": "uint32_t* r, const uint32_t* a, const uint32_t* b",
+    "lz_addw": "uint32_t* r, const uint32_t* a, const uint32_t* b", "lz_subw": "uint32_t* r, const uint32_t* a, const uint32_t* b",
+    "lz_addhi": "uint32_t* r, const uint32_t* x, const uint32_t* c", "lz_csubw": "uint32_t* r, const uint32_t* x, const uint32_t* k",
+    "lz_csub8": "uint32_t* r, const uint32_t* x, const uint32_t* k",
+}
+
+
 def limbs(x):
     return [(x >> (32 * i)) & MASK for i in range(N)]
 
@@ -403,6 +525,7 @@ def check(verbose=True, iters=3000):
         inp = {"x%d" % i: l for i, l in enumerate(limbs(a0))}
         inp.update({"y%d" % i: l for i, l in enumerate(limbs(b0))})
         assert sum(v << (32 * i) for i, v in enumerate(mw.run(inp))) == a0 * b0
+    check_leaves()
     if verbose:
         print("fp2_mul: %d IMAD.WIDE-equivalent pairs, %d add/sub/logic ops; fp2_sqr: %d pairs; all %d cases ok"
               % ((f2m.count("mad") + f2m.count("mul") - 16) // 2, f2m.count("add") + f2m.count("sub") + f2m.count("and") + f2m.count("selp"),
@@ -433,6 +556,9 @@ def render():
     out.append("// (r + q u) = (x + y u)^2\n"
                "__device__ __forceinline__ void fp2_sqr_ptx(uint32_t* r, uint32_t* q, const uint32_t* x, const uint32_t* y) {\n%s\n}\n"
                % gen_fp2_sqr().cuda())
+    out.append("// ---- leaf primitives of the lazily reduced tower (composed by csrc/lazy_gen.cuh)\n")
+    for prog in leaf_progs():
+        out.append("__device__ __forceinline__ void %s(%s) {\n%s\n}\n" % (prog.name, LEAF_SIGS[prog.name], prog.cuda()))
     return "\n".join(out)
 
 
