@@ -10,8 +10,13 @@
 
 namespace zkv {
 
-enum : uint8_t { F_INVALID = 1, F_SKIP0 = 2, F_SKIPC = 4, F_SKIPX = 8, F_SELMIS = 16 };
+enum : uint8_t { F_INVALID = 1, F_SKIP0 = 2, F_SKIPC = 4, F_SKIPX = 8, F_SELMIS = 16, F_BADDATA = 32 };   // (the pairing service reuses 0x20..0x80 as its own skip bits)
 enum : uint8_t { ST_OK = 0, ST_INVALID_INITIALIZATION = 1, ST_INVALID_PROOF_DATA = 2, ST_SELECTOR_MISMATCH = 3, ST_VERIFICATION_FAILED = 4 };
+
+// rejection status of a verification-path proof from its flags: the order of risc0/verifier.rs:151-170 and sp1/verifier.rs:64-83
+// (length < 4 -> InvalidProofData, selector, length != 260 -> InvalidProofData; k_decode sets exactly one of F_BADDATA / F_SELMIS)
+__device__ __forceinline__ uint8_t reject_status(uint8_t fl) { return (fl & F_BADDATA) ? ST_INVALID_PROOF_DATA : (fl & F_SELMIS) ? ST_SELECTOR_MISMATCH : ST_VERIFICATION_FAILED; }
+#define F_REJECT (F_INVALID | F_SELMIS | F_BADDATA)
 
 #define ZKV_WIN_BITS 4
 #define ZKV_WIN_PER_SCALAR 64          /* 256 / 4 */
@@ -47,17 +52,29 @@ __device__ __forceinline__ int g2_decode_bytes(fp2& x, fp2& y, const uint8_t* b)
     return g2_on_curve(x, y) ? 0 : 2;
 }
 
-// K1: decode (a, b, c) of one proof record.  rec + off points at 8 x BE-32.  vm == RISC0 applies
-// negate_g1 exactly as groth16.rs:75-84 does: on the raw 256-bit words, BEFORE any range check.
+// K1: decode (a, b, c) of one proof record.  Fixed-stride records: rec i at recs + i * stride.  Variable records (rec_off != nullptr: the
+// caller's concatenated seals / proofs uploaded as they are): rec i = recs + rec_off[i] - rec_base, length rec_off[i+1] - rec_off[i], and
+// the front checks of risc0/verifier.rs:151-170 / sp1/verifier.rs:64-83 happen HERE, in the reference's order: length < 4 ->
+// InvalidProofData, selector mismatch, length - 4 != 256 -> InvalidProofData (strict abi_decode of 8 x uint256).  rec + off points at
+// 8 x BE-32.  vm == RISC0 applies negate_g1 exactly as groth16.rs:75-84 does: on the raw 256-bit words, BEFORE any range check.
 __global__ void k_decode(int n, const uint8_t* recs, size_t stride, size_t off, uint32_t selector_le, int check_selector, int vm,
+                         const uint64_t* rec_off, uint64_t rec_base,
                          fp* ax, fp* ay, fp2* bx, fp2* by, fp* cx, fp* cy, uint8_t* flags) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint8_t* rec = recs + (size_t)i * stride;
+    const uint8_t* rec = rec_off ? recs + (size_t)(rec_off[i] - rec_base) : recs + (size_t)i * stride;
+    const uint64_t len = rec_off ? rec_off[i + 1] - rec_off[i] : (uint64_t)stride;
     uint8_t fl = 0;
-    if (check_selector) {
+    if (rec_off && len < 4) fl = F_BADDATA;
+    else if (check_selector) {
         uint32_t s = (uint32_t)rec[0] | (uint32_t)rec[1] << 8 | (uint32_t)rec[2] << 16 | (uint32_t)rec[3] << 24;
-        if (s != selector_le) fl |= F_SELMIS;
+        if (s != selector_le) fl = F_SELMIS;
+    }
+    if (rec_off && !fl && len != off + 256) fl = F_BADDATA;
+    if (fl) {                                             // never reaches the Groth16 stage: leave harmless operands for the uniform kernels behind
+        ax[i] = fp_zero(); ay[i] = fp_zero(); cx[i] = fp_zero(); cy[i] = fp_zero(); bx[i] = f2_zero(); by[i] = f2_zero();
+        flags[i] = fl | F_SKIP0 | F_SKIPC;
+        return;
     }
     const uint8_t* p = rec + off;
     uint32_t rx[8], ry[8];
@@ -107,7 +124,7 @@ __global__ void k_risc0_signals(int n, const uint8_t* image_ids, const uint8_t* 
 
 // K4: SP1 public signals (sp1/types.rs:21-38): s0 = U256_be(program_vkey), s1 = SHA256(pv) & (2^253 - 1).
 // A signal >= R makes the proof fail (groth16.rs:32-34); only s0 can be.
-__global__ void k_sp1_signals(int n, const uint8_t* vkeys, const uint8_t* pv, const uint64_t* pv_off, size_t pv_stride,
+__global__ void k_sp1_signals(int n, const uint8_t* vkeys, const uint8_t* pv, const uint64_t* pv_off, uint64_t pv_base, size_t pv_stride,
                               uint32_t* scal /* [n][2][8] */, uint8_t* flags) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -117,7 +134,7 @@ __global__ void k_sp1_signals(int n, const uint8_t* vkeys, const uint8_t* pv, co
     if (u256_geq(s0, C_R)) flags[i] |= F_INVALID;
     for (int k = 0; k < 8; k++) o[k] = s0[k];
     const uint8_t* msg; size_t len;
-    if (pv_off) { msg = pv + pv_off[i]; len = (size_t)(pv_off[i + 1] - pv_off[i]); } else { msg = pv + (size_t)i * pv_stride; len = pv_stride; }
+    if (pv_off) { msg = pv + (size_t)(pv_off[i] - pv_base); len = (size_t)(pv_off[i + 1] - pv_off[i]); } else { msg = pv + (size_t)i * pv_stride; len = pv_stride; }
     uint32_t h[8];
     sha256_msg(h, msg, len);
     h[0] &= 0x1fffffffu;
@@ -169,7 +186,7 @@ __global__ void k_g2_check(int n, const fp2* bx, const fp2* by, uint8_t* flags) 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint8_t fl = flags[i];
-    if (fl & (F_INVALID | F_SELMIS)) return;
+    if (fl & F_REJECT) return;
     fp2 x = bx[i], y = by[i];
     if (f2_is_zero(x) && f2_is_zero(y)) return;      // infinity is a member
     if (!g2_in_subgroup(x, y)) flags[i] = fl | F_INVALID;
@@ -234,7 +251,7 @@ __global__ void __launch_bounds__(ZKV_HTPB_MILLER, ZKV_MINBLOCKS_MILLER) k_mille
     uint8_t fl = flags[i];
     uint32_t skip = a.vk_skip;
     for (int j = 0; j < 3; j++) if (fl & a.skip_bit[j]) skip |= 1u << j;
-    if (fl & (F_INVALID | F_SELMIS)) skip = 0xF;
+    if (fl & F_REJECT) skip = 0xF;
     fp x12[2] = {a.px[1][i], a.px[2][i]}, y12[2] = {a.py[1][i], a.py[2][i]}, xy[2], iy[2];
     bool off[2] = {(skip & 2u) != 0, (skip & 4u) != 0};
     g1_slopes2(xy, iy, x12, y12, off);
@@ -255,7 +272,7 @@ __global__ void __launch_bounds__(ZKV_HTPB_MILLER, ZKV_MINBLOCKS_MILLER) k_mille
     uint8_t fl = flags[i];
     uint32_t skip = a.vk_skip;
     for (int j = 0; j < 3; j++) if (fl & a.skip_bit[j]) skip |= 1u << j;
-    if (fl & (F_INVALID | F_SELMIS)) skip = 0xF;
+    if (fl & F_REJECT) skip = 0xF;
     fp xy[2], iy[2];
     if (first) {
         fp x12[2] = {a.px[1][i], a.px[2][i]}, y12[2] = {a.py[1][i], a.py[2][i]};
@@ -284,8 +301,8 @@ __global__ void __launch_bounds__(ZKV_HTPB_FE, ZKV_MINBLOCKS_FE) k_final_exp(int
     fp12 m = in[i], gt;
     final_exp(gt, m);                                 // every thread runs it (k_miller left a harmless value for rejected inputs): uniform control flow
     if (i0 >= n) return;
-    if (fl & (F_INVALID | F_SELMIS)) {
-        status[i] = pairing_mode ? 2 : ((fl & F_SELMIS) ? ST_SELECTOR_MISMATCH : ST_VERIFICATION_FAILED);
+    if (fl & (pairing_mode ? (F_INVALID | F_SELMIS) : F_REJECT)) {
+        status[i] = pairing_mode ? 2 : reject_status(fl);
         if (gt_out) for (int k = 0; k < 384; k++) gt_out[(size_t)i * 384 + k] = 0;
         return;
     }
@@ -317,7 +334,7 @@ __global__ void __launch_bounds__(ZKV_HTPB_FE, ZKV_MINBLOCKS_FE) k_final_exp_sta
         final_exp_stage3(gt, f, x, y, z, t1);
         if (!w) return;
         uint8_t fl = flags[i];
-        if (fl & (F_INVALID | F_SELMIS)) { status[i] = (fl & F_SELMIS) ? ST_SELECTOR_MISMATCH : ST_VERIFICATION_FAILED; return; }
+        if (fl & F_REJECT) { status[i] = reject_status(fl); return; }
         status[i] = f12_is_one(gt) ? ST_OK : ST_VERIFICATION_FAILED;
     }
 }
@@ -339,7 +356,7 @@ __global__ void __launch_bounds__(LZ_NT, 2) k_miller_lz(int n, MillerArgs a, con
     const uint8_t fl = flags[i];
     uint32_t skip = a.vk_skip;
     for (int j = 0; j < 3; j++) if (fl & a.skip_bit[j]) skip |= 1u << j;
-    if (fl & (F_INVALID | F_SELMIS)) skip = 0xF;
+    if (fl & F_REJECT) skip = 0xF;
     fp* mysl = sl + 4 * (size_t)i0;
     if (first) lz_slopes_to(mysl, a.px[1] + i, a.py[1] + i, a.px[2] + i, a.py[2] + i, (skip & 2u) != 0, (skip & 4u) != 0);
     LzMillerIn in;
@@ -362,7 +379,7 @@ __global__ void __launch_bounds__(LZ_NT, 2) k_final_exp_lz(int n, int s_lo, int 
     for (int s = s_lo; s <= s_hi; s++) lz_final_exp_stage(s, in + i, st + 6 * (size_t)i0);
     if (s_hi < 3 || i0 >= n) return;
     const uint8_t fl = flags[i];
-    if (fl & (F_INVALID | F_SELMIS)) { status[i] = (fl & F_SELMIS) ? ST_SELECTOR_MISMATCH : ST_VERIFICATION_FAILED; return; }
+    if (fl & F_REJECT) { status[i] = reject_status(fl); return; }
     const uint32_t tid = lz_tid();
     fp one = fp_one(); uint32_t t = 0;
     for (int k = 0; k < 12; k++) { fp w = lz_ldfp(tid + (LZ_A + k) * LZ_SLOT); for (int j = 0; j < 8; j++) t |= w.v[j] ^ (k == 0 ? one.v[j] : 0u); }

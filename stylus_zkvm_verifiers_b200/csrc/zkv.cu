@@ -221,8 +221,10 @@ extern "C" int zkv_vk_load_sp1(const int* devices, int n_dev, zkv_vk** out) {
 enum SigMode { SIG_GENERIC, SIG_RISC0_VERIFY, SIG_RISC0_INTEGRITY, SIG_SP1 };
 struct Job {
     const zkv_vk* vk; size_t n;
-    // proof records (device): rec i at recs + i*stride, 8 x BE-32 at +off; selector (if any) in the first 4 bytes
+    // proof records (device): rec i at recs + i*stride (or at recs + rec_off[i] - rec_base when rec_off is set: the caller's concatenated
+    // blobs, front checks on the device), 8 x BE-32 at +off; selector (if any) in the first 4 bytes
     const uint8_t* recs; size_t stride, off; int check_selector; uint32_t selector_le;
+    const uint64_t* rec_off; uint64_t rec_base, pv_base;
     SigMode mode;
     const uint8_t *sig_a, *sig_b;           // generic: signals | risc0: image_ids, journals (or claims) | sp1: vkeys, public values
     const uint64_t* pv_off; size_t pv_stride; int k;
@@ -231,7 +233,7 @@ struct Job {
 };
 __global__ void k_status_all_fail(int n, const uint8_t* flags, uint8_t* status) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) status[i] = (flags[i] & F_SELMIS) ? ST_SELECTOR_MISMATCH : ST_VERIFICATION_FAILED;
+    if (i < n) status[i] = reject_status(flags[i]);
 }
 static std::atomic<unsigned long long> g_launches{0};   // kernels launched by the verification chains since load (bench.py's gpu_launches; a counter, not a setting)
 extern "C" unsigned long long zkv_launch_count(void) { return g_launches.load(); }
@@ -262,13 +264,13 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
     uint32_t* scal = c->scal + o * (size_t)ns * 8;
     uint8_t* flags = c->flags + o;
     if (timed) CK(cudaEventRecord(c->ev[0], s));
-    k_decode<<<nblk(m), TPB, 0, s>>>(m, j.recs + jo * j.stride, j.stride, j.off, j.selector_le, j.check_selector, vk->vm, c->px[0] + o, c->py[0] + o, c->qx + o, c->qy + o, c->px[3] + o, c->py[3] + o, flags);
+    k_decode<<<nblk(m), TPB, 0, s>>>(m, j.rec_off ? j.recs : j.recs + jo * j.stride, j.stride, j.off, j.selector_le, j.check_selector, vk->vm, j.rec_off ? j.rec_off + jo : nullptr, j.rec_base, c->px[0] + o, c->py[0] + o, c->qx + o, c->qy + o, c->px[3] + o, c->py[3] + o, flags);
     const g1aff* tab = c->d_tab; int nwin = ZKV_WIN_PER_SCALAR;
     switch (j.mode) {
         case SIG_GENERIC: k_generic_signals<<<nblk(m), TPB, 0, s>>>(m, j.k, j.sig_a + jo * (size_t)j.k * 32, scal, flags); break;
         case SIG_RISC0_VERIFY: k_risc0_signals<<<nblk(m), TPB, 0, s>>>(m, j.sig_a + jo * 32, j.sig_b + jo * 32, nullptr, 0, j.hc, scal); break;
         case SIG_RISC0_INTEGRITY: k_risc0_signals<<<nblk(m), TPB, 0, s>>>(m, nullptr, nullptr, j.sig_a + jo * 32, 1, j.hc, scal); break;
-        case SIG_SP1: k_sp1_signals<<<nblk(m), TPB, 0, s>>>(m, j.sig_a + jo * 32, j.pv_off ? j.sig_b : j.sig_b + jo * j.pv_stride, j.pv_off ? j.pv_off + jo : nullptr, j.pv_stride, scal, flags); break;
+        case SIG_SP1: k_sp1_signals<<<nblk(m), TPB, 0, s>>>(m, j.sig_a + jo * 32, j.pv_off ? j.sig_b : j.sig_b + jo * j.pv_stride, j.pv_off ? j.pv_off + jo : nullptr, j.pv_base, j.pv_stride, scal, flags); break;
     }
     if (j.mode == SIG_RISC0_VERIFY || j.mode == SIG_RISC0_INTEGRITY) { tab = c->d_tab + (size_t)2 * ZKV_WIN_PER_SCALAR * ZKV_WIN_ENTRIES; nwin = 32; }   // claim_lo / claim_hi are 128-bit
     if (timed) CK(cudaEventRecord(c->ev[1], s));
@@ -369,20 +371,29 @@ static int host_pipeline(DevCtx* c, const zkv_vk* vk, size_t m, size_t in_bytes,
     int rc = ctx_reserve(c, m, (size_t)ns * 8); if (rc) return rc;
     const int oc = vk->tune.overlap_chunks.load();
     int chunks = (m < (size_t)8192 || oc <= 1) ? 1 : oc;
-    rc = ctx_stage(c, in_bytes + 256 * (size_t)chunks, m); if (rc) return rc;
     size_t per = (m + chunks - 1) / chunks;
     per = (per + ZKV_HTPB - 1) / ZKV_HTPB * ZKV_HTPB;
-    size_t in_off = 0; int k = 0, used = 0;
-    for (size_t first = 0; first < m; first += per, k++) {
-        size_t cnt = std::min(per, m - first);
+    chunks = (int)((m + per - 1) / per);
+    // pack(first, cnt, nullptr) returns the size of a chunk's block, so every chunk's region of the pinned staging buffer is known up front
+    // and the chunks can be packed by concurrent host threads: chunk 0 on this thread, the others on helpers that are joined right before
+    // their chunk is enqueued.  Packing is a handful of bulk memcpy per chunk, i.e. memory-bandwidth work.
+    std::vector<size_t> bytes(chunks, 0), offs(chunks + 1, 0);
+    for (int k = 0; k < chunks; k++) { size_t first = per * (size_t)k; bytes[k] = pack(first, std::min(per, m - first), nullptr); offs[k + 1] = offs[k] + (bytes[k] + 255) / 256 * 256; }
+    (void)in_bytes;
+    rc = ctx_stage(c, offs[chunks], m); if (rc) return rc;
+    std::vector<std::thread> helpers;
+    for (int k = 1; k < chunks; k++) helpers.emplace_back([&, k]() { size_t first = per * (size_t)k; pack(first, std::min(per, m - first), c->h_pin + offs[k]); });
+    pack(0, std::min(per, m), c->h_pin);
+    int used = 0;
+    for (int k = 0; k < chunks; k++) {
+        const size_t first = per * (size_t)k, cnt = std::min(per, m - first), in_off = offs[k];
         cudaStream_t s = chunks == 1 ? c->stream : c->aux[k % DevCtx::NAUX];
         if (chunks > 1) used = std::max(used, k % DevCtx::NAUX + 1);
-        size_t bytes = pack(first, cnt, c->h_pin + in_off);
-        CK(cudaMemcpyAsync(c->d_in + in_off, c->h_pin + in_off, bytes, cudaMemcpyHostToDevice, s));
-        Job j = job(first, cnt, c->d_in + in_off);
-        rc = enqueue_chain(c, j, 0, first, (int)cnt, s, chunks == 1); if (rc) return rc;
-        CK(cudaMemcpyAsync(c->h_out + first, c->d_out + first, cnt, cudaMemcpyDeviceToHost, s));
-        in_off += (bytes + 255) / 256 * 256;
+        if (k) helpers[k - 1].join();
+        rc = cudaMemcpyAsync(c->d_in + in_off, c->h_pin + in_off, bytes[k], cudaMemcpyHostToDevice, s) == cudaSuccess ? 0 : fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (host to device)");
+        if (!rc) { Job j = job(first, cnt, c->d_in + in_off); rc = enqueue_chain(c, j, 0, first, (int)cnt, s, chunks == 1); }
+        if (!rc && cudaMemcpyAsync(c->h_out + first, c->d_out + first, cnt, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (device to host)");
+        if (rc) { for (int t = k; t < chunks - 1; t++) helpers[t].join(); return rc; }
     }
     if (chunks == 1) { CK(cudaStreamSynchronize(c->stream)); collect_stage_ms(c); }
     else for (int a = 0; a < used; a++) CK(cudaStreamSynchronize(c->aux[a]));
@@ -429,7 +440,7 @@ extern "C" int zkv_groth16_verify_batch(const zkv_vk* vk, const uint8_t* proofs,
             size_t m = std::min(MAX_CHUNK, e - s0);
             int rc = host_pipeline(c, vk, m, m * (256 + (size_t)k * 32), k,
                 [&](size_t first, size_t cnt, uint8_t* dst) -> size_t {
-                    memcpy(dst, proofs + (s0 + first) * 256, cnt * 256); memcpy(dst + cnt * 256, signals + (s0 + first) * (size_t)k * 32, cnt * (size_t)k * 32);
+                    if (dst) { memcpy(dst, proofs + (s0 + first) * 256, cnt * 256); memcpy(dst + cnt * 256, signals + (s0 + first) * (size_t)k * 32, cnt * (size_t)k * 32); }
                     return cnt * (256 + (size_t)k * 32);
                 },
                 [&](size_t first, size_t cnt, uint8_t* d) -> Job {
@@ -530,50 +541,45 @@ extern "C" int zkv_risc0_get_control_root(const zkv_risc0* h, uint8_t out0[16], 
 extern "C" int zkv_risc0_get_bn254_control_id(const zkv_risc0* h, uint8_t out[32]) { if (!h || !out) return fail(ZKV_ERR_ARG, "null"); if (h->initialized) memcpy(out, h->bn254_control_id, 32); else memset(out, 0, 32); return 0; }
 extern "C" int zkv_risc0_get_verifier_key_digest(const zkv_risc0* h, uint8_t out[32]) { if (!h || !out) return fail(ZKV_ERR_ARG, "null"); risc0_vk_digest(out, h->vk); return 0; }
 
-// Host-side front checks shared by RISC Zero and SP1 (risc0/verifier.rs:151-170, sp1/verifier.rs:64-83):
-// returns the indices that reach the Groth16 stage; everything else gets its final status here.
+static uint32_t sel_le(const uint8_t s[4]) { return (uint32_t)s[0] | (uint32_t)s[1] << 8 | (uint32_t)s[2] << 16 | (uint32_t)s[3] << 24; }
 static bool offsets_ok(const uint64_t* off, size_t n) { for (size_t i = 0; i < n; i++) if (off[i + 1] < off[i]) return false; return true; }
-static void front_filter(const uint8_t* blobs, const uint64_t* off, size_t n, const uint8_t selector[4], uint8_t* status_out, std::vector<uint32_t>& cand) {
-    cand.clear(); cand.reserve(n);
-    for (size_t i = 0; i < n; i++) {
-        uint64_t len = off[i + 1] - off[i]; const uint8_t* p = blobs + off[i];
-        if (len < 4) { status_out[i] = ZKV_INVALID_PROOF_DATA; continue; }
-        if (memcmp(p, selector, 4) != 0) { status_out[i] = ZKV_SELECTOR_MISMATCH; continue; }
-        if (len - 4 != 256) { status_out[i] = ZKV_INVALID_PROOF_DATA; continue; }        // strict abi_decode of 8 x uint256
-        cand.push_back((uint32_t)i);
-    }
-}
-
+// Host-buffer batches upload the caller's arrays AS THEY ARE (four bulk copies per chunk into pinned staging: offsets, the two 32-byte
+// arrays, the seal bytes) and leave the front checks of verify_integrity_internal (risc0/verifier.rs:151-170) to k_decode; round 1
+// filtered and repacked proof by proof on the host, which cost 7 % of the end-to-end rate.
 static int risc0_batch(const zkv_risc0* h, const uint8_t* seals, const uint64_t* seal_off, const uint8_t* a32, const uint8_t* b32, int integrity, size_t n, uint8_t* status_out) {
     if (!h || (n && (!seals || !seal_off || !a32 || (!integrity && !b32) || !status_out))) return fail(ZKV_ERR_ARG, "zkv_risc0_verify_batch: null argument");
     if (n == 0) return 0;
     if (n > 0xffffffffull) return fail(ZKV_ERR_ARG, "batch too large");
     if (!offsets_ok(seal_off, n)) return fail(ZKV_ERR_ARG, "seal offsets must be non-decreasing");
     if (!h->initialized) { memset(status_out, ZKV_INVALID_INITIALIZATION, n); return 0; }     // risc0/verifier.rs:84-86, 99-101
-    std::vector<uint32_t> cand; front_filter(seals, seal_off, n, h->selector, status_out, cand);
     const zkv_vk* vk = h->vk;
-    return for_each_device(vk, cand.size(), [&](DevCtx* c, size_t b, size_t e) -> int {
+    return for_each_device(vk, n, [&](DevCtx* c, size_t b, size_t e) -> int {
         for (size_t s0 = b; s0 < e; s0 += MAX_CHUNK) {
             size_t m = std::min(MAX_CHUNK, e - s0);
             const size_t per = integrity ? 32 : 64;
-            int rc = host_pipeline(c, vk, m, m * (256 + per), 2,
+            const size_t blob = (size_t)(seal_off[s0 + m] - seal_off[s0]);
+            // chunk block layout: [offsets (cnt + 1) x 8][a32 cnt x 32][b32 cnt x 32][seal bytes][slack: k_decode never reads past a record's own length]
+            int rc = host_pipeline(c, vk, m, blob + m * (8 + per) + 64 * 8 + 64 * 320, 2,
                 [&](size_t first, size_t cnt, uint8_t* dst) -> size_t {
-                    uint8_t* pa = dst + cnt * 256; uint8_t* pb = pa + cnt * 32;
-                    for (size_t t = 0; t < cnt; t++) {
-                        size_t i = cand[s0 + first + t];
-                        memcpy(dst + t * 256, seals + seal_off[i] + 4, 256); memcpy(pa + t * 32, a32 + i * 32, 32);
-                        if (!integrity) memcpy(pb + t * 32, b32 + i * 32, 32);
-                    }
-                    return cnt * (256 + per);
+                    const size_t i0 = s0 + first, bytes = (size_t)(seal_off[i0 + cnt] - seal_off[i0]);
+                    if (!dst) return (cnt + 1) * 8 + cnt * per + bytes + 320;
+                    uint8_t* p = dst;
+                    memcpy(p, seal_off + i0, (cnt + 1) * 8); p += (cnt + 1) * 8;
+                    memcpy(p, a32 + i0 * 32, cnt * 32); p += cnt * 32;
+                    if (!integrity) { memcpy(p, b32 + i0 * 32, cnt * 32); p += cnt * 32; }
+                    memcpy(p, seals + seal_off[i0], bytes); p += bytes;
+                    return (size_t)(p - dst) + 320;
                 },
                 [&](size_t first, size_t cnt, uint8_t* d) -> Job {
                     Job j; memset(&j, 0, sizeof j);
-                    j.vk = vk; j.n = cnt; j.recs = d; j.stride = 256; j.off = 0; j.mode = integrity ? SIG_RISC0_INTEGRITY : SIG_RISC0_VERIFY;
-                    j.sig_a = d + cnt * 256; j.sig_b = d + cnt * 288; j.hc = h->hc; j.base = h->base; j.all_fail = h->all_fail; j.d_status = c->d_out + first;
+                    j.vk = vk; j.n = cnt; j.rec_off = (const uint64_t*)d; j.rec_base = seal_off[s0 + first]; j.off = 4; j.stride = 260; j.check_selector = 1; j.selector_le = sel_le(h->selector);
+                    j.mode = integrity ? SIG_RISC0_INTEGRITY : SIG_RISC0_VERIFY;
+                    j.sig_a = d + (cnt + 1) * 8; j.sig_b = j.sig_a + cnt * 32; j.recs = j.sig_a + cnt * per;
+                    j.hc = h->hc; j.base = h->base; j.all_fail = h->all_fail; j.d_status = c->d_out + first;
                     return j;
                 });
             if (rc) return rc;
-            for (size_t t = 0; t < m; t++) status_out[cand[s0 + t]] = c->h_out[t];
+            memcpy(status_out + s0, c->h_out, m);
         }
         return 0;
     });
@@ -592,7 +598,6 @@ extern "C" int zkv_risc0_verify_integrity(const zkv_risc0* h, const uint8_t* sea
     uint64_t off[2] = {0, seal_len}; uint8_t dummy = 0;
     return risc0_batch(h, seal ? seal : &dummy, off, claim_digest, nullptr, 1, 1, status_out);
 }
-static uint32_t sel_le(const uint8_t s[4]) { return (uint32_t)s[0] | (uint32_t)s[1] << 8 | (uint32_t)s[2] << 16 | (uint32_t)s[3] << 24; }
 extern "C" int zkv_risc0_verify_batch_device(const zkv_risc0* h, int device, const void* d_seals260, const void* d_image_ids, const void* d_journal_digests, size_t n, void* d_status_out, void* stream) {
     if (!h || !d_seals260 || !d_image_ids || !d_journal_digests || !d_status_out) return fail(ZKV_ERR_ARG, "zkv_risc0_verify_batch_device: null argument");
     DevCtx* c = vk_ctx(h->vk, device);
@@ -631,33 +636,35 @@ extern "C" int zkv_sp1_verify_batch(const zkv_sp1* h, const uint8_t* vkeys, cons
     if (n == 0) return 0;
     if (n > 0xffffffffull) return fail(ZKV_ERR_ARG, "batch too large");
     if (!offsets_ok(proof_off, n) || !offsets_ok(pv_off, n)) return fail(ZKV_ERR_ARG, "proof / public-value offsets must be non-decreasing");
-    std::vector<uint32_t> cand; front_filter(proofs, proof_off, n, h->verifier_hash, status_out, cand);
     const zkv_vk* vk = h->vk;
-    return for_each_device(vk, cand.size(), [&](DevCtx* c, size_t b, size_t e) -> int {
+    return for_each_device(vk, n, [&](DevCtx* c, size_t b, size_t e) -> int {
         for (size_t s0 = b; s0 < e; s0 += MAX_CHUNK) {
             size_t m = std::min(MAX_CHUNK, e - s0);
-            size_t pvb = 0; for (size_t t = 0; t < m; t++) { size_t i = cand[s0 + t]; pvb += pv_off[i + 1] - pv_off[i]; }
-            // chunk block layout: [proofs cnt x 256][vkeys cnt x 32][offsets (cnt + 1) x 8][public values]
-            int rc = host_pipeline(c, vk, m, m * (256 + 32 + 8) + 8 * 64 + pvb, 2,
+            const size_t pvb = (size_t)(pv_off[s0 + m] - pv_off[s0]), prb = (size_t)(proof_off[s0 + m] - proof_off[s0]);
+            // chunk block layout: [proof offsets (cnt + 1) x 8][public-value offsets (cnt + 1) x 8][vkeys cnt x 32][proof bytes][public values][slack]
+            int rc = host_pipeline(c, vk, m, prb + pvb + m * (16 + 32) + 64 * 16 + 64 * 320, 2,
                 [&](size_t first, size_t cnt, uint8_t* dst) -> size_t {
-                    uint8_t* pk = dst + cnt * 256; uint64_t* po = (uint64_t*)(pk + cnt * 32); uint8_t* pp = (uint8_t*)(po + cnt + 1);
-                    uint64_t acc = 0;
-                    for (size_t t = 0; t < cnt; t++) {
-                        size_t i = cand[s0 + first + t]; uint64_t len = pv_off[i + 1] - pv_off[i];
-                        memcpy(dst + t * 256, proofs + proof_off[i] + 4, 256); memcpy(pk + t * 32, vkeys + i * 32, 32);
-                        po[t] = acc; memcpy(pp + acc, public_values + pv_off[i], len); acc += len;
-                    }
-                    po[cnt] = acc;
-                    return cnt * (256 + 32) + (cnt + 1) * 8 + acc;
+                    const size_t i0 = s0 + first, pr = (size_t)(proof_off[i0 + cnt] - proof_off[i0]), pv = (size_t)(pv_off[i0 + cnt] - pv_off[i0]);
+                    if (!dst) return (cnt + 1) * 16 + cnt * 32 + pr + pv + 320;
+                    uint8_t* p = dst;
+                    memcpy(p, proof_off + i0, (cnt + 1) * 8); p += (cnt + 1) * 8;
+                    memcpy(p, pv_off + i0, (cnt + 1) * 8); p += (cnt + 1) * 8;
+                    memcpy(p, vkeys + i0 * 32, cnt * 32); p += cnt * 32;
+                    memcpy(p, proofs + proof_off[i0], pr); p += pr;
+                    memcpy(p, public_values + pv_off[i0], pv); p += pv;
+                    return (size_t)(p - dst) + 320;
                 },
                 [&](size_t first, size_t cnt, uint8_t* d) -> Job {
+                    const size_t i0 = s0 + first;
                     Job j; memset(&j, 0, sizeof j);
-                    j.vk = vk; j.n = cnt; j.recs = d; j.stride = 256; j.off = 0; j.mode = SIG_SP1; j.sig_a = d + cnt * 256;
-                    j.pv_off = (const uint64_t*)(d + cnt * 288); j.sig_b = d + cnt * 288 + (cnt + 1) * 8; j.base = c->h_ic0; j.d_status = c->d_out + first;
+                    j.vk = vk; j.n = cnt; j.rec_off = (const uint64_t*)d; j.rec_base = proof_off[i0]; j.off = 4; j.stride = 260; j.check_selector = 1; j.selector_le = sel_le(h->verifier_hash);
+                    j.mode = SIG_SP1; j.pv_off = (const uint64_t*)(d + (cnt + 1) * 8); j.pv_base = pv_off[i0];
+                    j.sig_a = d + (cnt + 1) * 16; j.recs = j.sig_a + cnt * 32; j.sig_b = j.recs + (size_t)(proof_off[i0 + cnt] - proof_off[i0]);
+                    j.base = c->h_ic0; j.d_status = c->d_out + first;
                     return j;
                 });
             if (rc) return rc;
-            for (size_t t = 0; t < m; t++) status_out[cand[s0 + t]] = c->h_out[t];
+            memcpy(status_out + s0, c->h_out, m);
         }
         return 0;
     });

@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Condense ncu reports into the JSON committed under profiles/: python tools/ncu_summary.py out.json report1.ncu-rep [report2 ...]
-(per kernel: duration, launch shape, pipe / issue utilisation, stall ratios, local-memory traffic, DRAM bytes; for k_miller and
-k_final_exp also the executed opcode mix and the stall-sample shares from the source page)."""
+(per kernel: duration, launch shape, pipe / issue utilisation incl. the fmaheavy / alu pipe counters, stall ratios, local-memory traffic,
+DRAM bytes; for the Miller-loop and final-exponentiation kernels also the executed opcode mix with per-proof executed counts, the
+EXECUTED IMAD.WIDE share of the multiplier issue rate and the stall-sample shares from the source page)."""
 import collections, csv, io, json, re, subprocess, sys
 
 WANT = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -10,7 +11,11 @@ WANT = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
         "sass__inst_executed_local_loads", "sass__inst_executed_local_stores", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+        "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fmalite_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fmaheavy.sum", "sm__inst_executed_pipe_fmalite.sum",
+        "sm__inst_executed_pipe_alu.sum", "sm__inst_executed.sum", "sm__cycles_active.avg", "launch__shared_mem_per_block_dynamic"]
+HEAVY = ("k_miller", "k_miller_norm", "k_final_exp", "k_miller_lz", "k_final_exp_lz", "k_miller_norm_seg", "k_final_exp_stage", "k_lz", "k_old", "k_pairing_lz")
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
@@ -28,12 +33,13 @@ def source_mix(rep, kernel):
             continue
         seen.add(r[0])
         m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[ix["Source"]]); op = m.group(2) if m else "?"
-        cls = "IMAD.WIDE" if op.startswith("IMAD.WIDE") else op.split(".")[0]
+        cls = "IMAD.WIDE" if op.startswith("IMAD.WIDE") else ("IMAD.other" if op.startswith("IMAD") else op.split(".")[0])
         ex[cls] += int(float(r[ix["Instructions Executed"]] or 0))
         for s in stalls:
             st[s[6:]] += int(float(r[ix[s]] or 0))
     T, S = sum(ex.values()), sum(st.values())
-    return {"executed_warp_instructions": T, "opcode_share": {k: round(v / T, 4) for k, v in ex.most_common(10)}, "stall_sample_share": {k: round(v / S, 4) for k, v in st.most_common(8)}}
+    return {"executed_warp_instructions": T, "executed_imad_wide_warp_instructions": ex["IMAD.WIDE"], "opcode_share": {k: round(v / T, 4) for k, v in ex.most_common(12)},
+            "stall_sample_share": {k: round(v / S, 4) for k, v in st.most_common(8)}}
 
 
 def main(out, reps):
@@ -53,13 +59,17 @@ def main(out, reps):
             for key, col in (("dram_bytes_read", "dram__bytes_read.sum"), ("dram_bytes_write", "dram__bytes_write.sum")):
                 d[key] = float(r[ix[col]].replace(",", "")) * SCALE.get(units[ix[col]], 1)
             d["proofs"] = int(d.get("launch__grid_size", 0) * d.get("launch__block_size", 0))
-            if name in ("k_miller", "k_miller_norm", "k_final_exp") and d["proofs"] >= 1024:
-                d["source_page"] = source_mix(rep, name)
+            if name in HEAVY and d["proofs"] >= 1024:
+                sp = d["source_page"] = source_mix(rep, name)
+                # executed IMAD.WIDE per thread (= per proof for full blocks) and their share of the multiplier issue rate: one IMAD.WIDE per 4
+                # cycles per scheduler, 4 schedulers per SM => peak = 1 warp-instruction per cycle per SM
+                sp["executed_imad_wide_per_proof"] = round(sp["executed_imad_wide_warp_instructions"] * 32 / d["proofs"])
+                sms, cyc = 148, d.get("sm__cycles_active.avg [cycle]")
+                if cyc:
+                    sp["executed_imad_wide_frac_of_issue_peak"] = round(sp["executed_imad_wide_warp_instructions"] / (sms * cyc), 4)
             kernels.append(d)
-    json.dump({"source": "ncu --set full --import-source on --clock-control none ... python bench.py --steps 1 --warmup 3 --no-cpu-baseline [--chunks 1] (2^16 RISC Zero-shape proofs): "
-                         "the one-kernel forms (k_vkx, k_g2_check, k_miller_norm, k_final_exp) come from the serial single-chain pass (--chunks 1, report *_serial), the segment / stage kernels "
-                         "(k_miller_norm_seg, k_final_exp_stage: one chunk of 2^15 proofs, in launch order) from the default chunked path (report *_chunked); tools/profile_r1.sh is the recipe; "
-                         "the .ncu-rep files (60 MB each) are not kept",
+    json.dump({"source": "ncu --set full --metrics <fmaheavy / fmalite / alu pipe counters> --import-source on --clock-control none (recipes: tools/profile_r2.sh for bench.py --chunks 1 at 2^16 "
+                         "RISC Zero-shape proofs, tools/r2_lzbench.sh for the layout microbenchmark); the .ncu-rep files are not kept",
                "note": "per-launch times under ncu are serialised and cold-cache: bench.py's live CUDA-event timings are the reported figures.  IMAD.WIDE issues once per 4 cycles "
                        "per scheduler, so a 25 % issue share of IMAD.WIDE would be 100 % of the integer-multiply roofline.",
                "kernels": kernels}, open(out, "w"), indent=1)
