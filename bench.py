@@ -31,17 +31,31 @@ W_RISC0_M = W_MILLER3_M + W_FINALEXP_M + 1800 + 40 + 1000
 W_SP1_M = W_MILLER3_M + W_FINALEXP_M + 1800 + 40 + 1700
 
 
-def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` at this workload, from the committed ncu --set full summary
-    (profiles/r1_ncu_summary.json); None if the summary is absent."""
-    try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))
-        for k in d["kernels"]:
-            if k["kernel"] == kernel and "source_page" in k:
-                return {"bytes_per_launch": k["dram_bytes_read"] + k["dram_bytes_write"], "proofs_per_launch": k["proofs"], "source": "profiles/r1_ncu_summary.json"}
-    except Exception:
-        pass
+def ncu_summary(kernel):
+    """The committed ncu --set full summary of one launch of `kernel` at this workload (profiles/r2_ncu_summary.json for the shared-memory
+    kernels, profiles/r1_ncu_summary.json for the round-1 kernels): DRAM traffic per launch, EXECUTED IMAD.WIDE per proof and the pipe
+    counters.  None if absent."""
+    for name in ("r2_ncu_summary.json", "r1_ncu_summary.json"):
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", name)))
+            for k in d["kernels"]:
+                if k["kernel"] == kernel and "source_page" in k:
+                    sp = k["source_page"]
+                    per_proof = sp.get("executed_imad_wide_per_proof") or round(sp["executed_warp_instructions"] * sp["opcode_share"].get("IMAD.WIDE", 0) * 32 / k["proofs"])
+                    return {"traffic": {"bytes_per_launch": k["dram_bytes_read"] + k["dram_bytes_write"], "proofs_per_launch": k["proofs"], "source": "profiles/" + name},
+                            "executed_imad_wide_per_proof": per_proof,
+                            "ncu_fmaheavy_pct": k.get("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active [%]"),
+                            "ncu_executed_imad_wide_frac": sp.get("executed_imad_wide_frac_of_issue_peak")}
+        except Exception:
+            pass
     return None
+
+
+def workload_config(shape, n):
+    """`config` of the JSON line: the workload only, shared verbatim by this repo's arm and the --impl reference arm"""
+    return {"workload": "%s: 2^%d synthetic %s-shape Groth16 proofs per GPU per step (%d public inputs, fixed random vk, trapdoor-simulated, all valid)" %
+            ("configs[1]" if shape == "risc0" else "configs[2] shape", n.bit_length() - 1, "RISC Zero" if shape == "risc0" else "SP1 v5", 5 if shape == "risc0" else 2),
+            "proofs_per_gpu": n, "sharding": "contiguous proof ranges, no collective"}
 
 
 def dist_env():
@@ -146,8 +160,8 @@ def run_reference(args, rank, world):
     ro = O.Risc0Oracle(O.Vk(0, vk.alpha, vk.beta, vk.gamma, vk.delta, vk.ic))
     r = consts["risc0_fixture"]
     ro.initialize(h(r["control_root"]), h(r["bn254_control_id"]))
-    m = max(64, 24 * cores)             # bounded sample per step
-    b = S.make_risc0_batch(OB(), vk, ro.selector(), h(r["control_root"]), h(r["bn254_control_id"]), h(consts["risc0_system_state_zero_digest"]), m, 0xB2000001, pool=64)
+    m = 4096                            # bounded sample per step: the first 4096 proofs of the same seeded workload (about 1 s on 16 threads)
+    b = S.make_risc0_batch(OB(), vk, ro.selector(), h(r["control_root"]), h(r["bn254_control_id"]), h(consts["risc0_system_state_zero_digest"]), m, 0xB2000001, pool=256)
     for _ in range(args.warmup):
         ro.verify_batch(b.seals, b.image_ids, b.journals)
     t0 = time.perf_counter()
@@ -158,9 +172,10 @@ def run_reference(args, rank, world):
     val = m * args.steps / dt
     line = {"impl": "reference", "metric": "groth16_verifies_per_sec", "value": val, "unit": "verifies/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u256 (4x64-bit Montgomery)",
-            "data": "synthetic", "config": {"workload": "configs[1]: synthetic RISC Zero-shape Groth16 proofs (5 public inputs, fixed random vk); bounded sample of %d proofs per step" % m},
+            "data": "synthetic", "config": workload_config("risc0", args.n),
             "cpu_baseline": {"value": val, "unit": "verifies/s", "cores": cores, "kind": "port",
-                             "sample": "%d proofs x %d steps, oracle/zkv_oracle.c (C restatement of the reference path; Rust reference not buildable here) under OpenMP" % (m, args.steps)},
+                             "sample": "each step = a bounded sample of %d proofs of the configured workload (same key seed, same generator), %d steps; oracle/zkv_oracle.c (C restatement of the "
+                                       "reference path; the Rust reference cannot be built here) under OpenMP on all %d host threads" % (m, args.steps, cores)},
             "e2e": {"value": val, "unit": "verifies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -312,24 +327,33 @@ def main():
     mac_miller = miller_n * W_MILLER3_M * M_MAC32
     serial_miller_ms = stage_sum.get("miller", 0.0)
     miller_kernel = "k_miller" if args.exact_lines else ("k_miller_lz" if layout else "k_miller_norm")    # verification path: normalised gamma / delta lines by default
+    ncu = ncu_summary(miller_kernel) or {}
+    ncu_fe = ncu_summary("k_final_exp_lz" if layout else "k_final_exp") or {}
+    exec_pp, exec_fe_pp = ncu.get("executed_imad_wide_per_proof"), ncu_fe.get("executed_imad_wide_per_proof")
     line = {
         "metric": "groth16_verifies_per_sec", "value": value, "unit": "verifies/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u256 (8x32-bit Montgomery limbs, IMAD.WIDE.U32)", "data": "synthetic",
-        "config": {"workload": "%s: 2^%d synthetic %s-shape Groth16 proofs per GPU per step (%d public inputs, fixed random vk, trapdoor-simulated, all valid)" %
-                   ("configs[1]" if args.shape == "risc0" else "configs[2] shape", n.bit_length() - 1, "RISC Zero" if args.shape == "risc0" else "SP1 v5", 5 if args.shape == "risc0" else 2),
-                   "proofs_per_gpu": n, "l2": "flushed between timed steps (256 MiB fill)", "sharding": "contiguous proof ranges, no collective",
-                   "overlap": "%d chunks per device batch on side streams (stage_ms: serial single-chain pass over all proofs; roofline: serial single-chain launches of a whole number of waves)" % chunks},
+        "config": workload_config(args.shape, n),
+        "execution": {"l2": "flushed between timed steps (256 MiB fill)", "layout": "shared-memory-resident lazily reduced kernels" if layout else "round-1 thread-stack kernels",
+                      "overlap": "%d chunks per device batch on side streams (stage_ms: serial single-chain pass over all proofs; roofline: serial single-chain launches of a whole number of waves)" % chunks},
         "e2e": {"value": total / e2e_s, "unit": "verifies/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": n},
         "gpu_launches": launches,
         "stage_ms": stage_sum,
         "roofline": {"bound": "imad", "bound_note": "integer-multiply (IMAD.WIDE) issue rate; neither HBM nor the tensor cores bound this path (SURVEY 8d)", "kernel": miller_kernel, "achieved": mac_miller / (miller_ms * 1e-3) / 1e12 if miller_ms else None, "peak": imad_peak / 1e12,
-                     "unit": "TMAC32/s", "frac": (mac_miller / (miller_ms * 1e-3)) / imad_peak if miller_ms else None, "traffic": ncu_traffic(miller_kernel),
+                     "unit": "TMAC32/s", "frac": (mac_miller / (miller_ms * 1e-3)) / imad_peak if miller_ms else None, "traffic": ncu.get("traffic"),
+                     "frac_note": "frac = SURVEY 8d's FIXED work per proof (136 MAC32 per Fp multiplication, no credit taken away for algorithmic savings) / time / peak; executed_frac = IMAD.WIDE "
+                                  "instructions actually executed per proof (ncu source page of the same kernel, profiles/) x proofs / time / peak = the multiplier pipe's issue utilisation",
+                     "executed_imad_wide_per_proof": exec_pp,
+                     "executed_frac": (miller_n * exec_pp / (miller_ms * 1e-3)) / imad_peak if (miller_ms and exec_pp) else None,
+                     "final_exp_executed_imad_wide_per_proof": exec_fe_pp,
+                     "final_exp_executed_frac": (fe_n * exec_fe_pp / (fe_ms * 1e-3)) / imad_peak if (fe_ms and exec_fe_pp) else None,
+                     "ncu_fmaheavy_pct": {"miller": ncu.get("ncu_fmaheavy_pct"), "final_exp": ncu_fe.get("ncu_fmaheavy_pct")},
                      "peak_source": "IMAD.WIDE.U32 issue rate measured live on this GPU (zkv_imad_peak); MEASURED_PEAKS.json holds no integer figure",
                      "fpmul_chain_per_s": fpmul_peak,
                      "whole_path_frac": value / world * W_M * M_MAC32 / imad_peak,
                      "final_exp_frac": (fe_n * W_FINALEXP_M * M_MAC32 / (fe_ms * 1e-3)) / imad_peak if fe_ms else None,
-                     "launch": {"proofs": miller_n, "ms": miller_ms, "note": "one k_miller_norm launch over a whole number of its waves (prefix of the batch), serial chain, CUDA events on the launching stream"},
+                     "launch": {"proofs": miller_n, "ms": miller_ms, "note": "one " + miller_kernel + " launch over a whole number of its waves (prefix of the batch), serial chain, CUDA events on the launching stream"},
                      "final_exp_launch": {"proofs": fe_n, "ms": fe_ms},
                      "frac_serial_all_proofs": (n * W_MILLER3_M * M_MAC32 / (serial_miller_ms * 1e-3)) / imad_peak if serial_miller_ms else None},
         "clocks": clocks.summary(),

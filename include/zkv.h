@@ -119,6 +119,14 @@ int zkv_pairing4_batch(const zkv_vk* vk, const uint8_t* g1s, const uint8_t* g2s,
 int zkv_pairing4_batch_device(const zkv_vk* vk, int device, const void* d_g1s, const void* d_g2s, size_t n,
                               void* d_ok_out, void* d_gt_out, void* stream);
 
+/* General ecPairing (precompile 0x08, the seam the reference calls at common/groth16.rs:109-128): n instances of a k-pair product check
+ * with EVERY G2 point variable.  in: n x k x 192 B, each pair G1 (64 B) || G2 (128 B, wire order).  out: n x 32 B, the precompile's return
+ * word (0..01 / 0..00).  reverted[i] = 1 where the call would fail (coordinate >= p, point off its curve, G2 point outside the order-r
+ * subgroup); a pair with a member at infinity contributes 1; k = 0 is the empty product (true).  miller_out (optional, n x 384 B): the
+ * Miller-loop value in the oracle's convention.  zkv_ec_pairing is one call on raw bytes (len % 192 != 0 -> reverted). */
+int zkv_ec_pairing_batch(const uint8_t* in, int k, size_t n, uint8_t* out, uint8_t* reverted, uint8_t* miller_out, int device);
+int zkv_ec_pairing(const uint8_t* in, size_t len, uint8_t out[32], uint8_t* reverted, int device);
+
 /* ---- precompile-shaped batched services (the L1 seam, common/groth16.rs:60-73: ec_call) -----
  * zkv_ec_add_batch: n x 128 B (x1,y1,x2,y2) -> n x 64 B, EIP-196 0x06 (groth16.rs:55).
  * zkv_ec_mul_batch: n x 96 B (x,y,s)        -> n x 64 B, EIP-196 0x07 (groth16.rs:54).

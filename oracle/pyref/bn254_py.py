@@ -332,3 +332,34 @@ def risc0_selector(control_root, bn254_control_id, vk):
     d = sha256(sha256(b"risc0.Groth16ReceiptVerifierParameters") + control_root + bn254_control_id[::-1]
                + risc0_vk_digest(vk) + b"\x03\x00")
     return d[:4]
+
+
+# ---------------------------------------------------------------- the two verifiers' control flow, as status codes (0 ok, 2 InvalidProofData,
+# 3 SelectorMismatch / WrongVerifierSelector, 4 VerificationFailed): restated from the reference independently of oracle/zkv_oracle.c
+ST_OK, ST_INVALID_PROOF_DATA, ST_SELECTOR_MISMATCH, ST_VERIFICATION_FAILED = 0, 2, 3, 4
+
+
+def _front(seal, selector):
+    """risc0/verifier.rs:151-170 and sp1/verifier.rs:64-83: length < 4, selector, then strict abi_decode of 8 x uint256"""
+    if len(seal) < 4: return ST_INVALID_PROOF_DATA, None
+    if seal[:4] != selector: return ST_SELECTOR_MISMATCH, None
+    if len(seal) - 4 != 256: return ST_INVALID_PROOF_DATA, None
+    return None, [_be(seal[4 + 32 * i:36 + 32 * i]) for i in range(8)]
+
+
+def risc0_verify_status(vk, selector, control_root, bn254_control_id, seal, image_id, journal_digest):
+    """RiscZeroVerifier::verify of an initialised verifier (risc0/verifier.rs:78-92, 146-197)"""
+    st, w = _front(seal, selector)
+    if st is not None: return st
+    c0, c1 = split_digest(control_root)
+    lo, hi = split_digest(risc0_claim_digest(image_id, journal_digest))
+    sig = [_be(c0), _be(c1), _be(lo), _be(hi), _be(bn254_control_id)]
+    return ST_OK if groth16_verify(RISC0, vk, w[0:2], [w[2:4], w[4:6]], w[6:8], sig) else ST_VERIFICATION_FAILED
+
+
+def sp1_verify_status(vk, selector, vkey, public_values, proof):
+    """Sp1Verifier::verify_proof (sp1/verifier.rs:58-111, sp1/types.rs:21-38)"""
+    st, w = _front(proof, selector)
+    if st is not None: return st
+    sig = [_be(vkey), _be(sha256(public_values)) & ((1 << 253) - 1)]
+    return ST_OK if groth16_verify(SP1, vk, w[0:2], [w[2:4], w[4:6]], w[6:8], sig) else ST_VERIFICATION_FAILED

@@ -43,6 +43,8 @@ _SIGS = {
     "zkv_sp1_verify_batch_device": (C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P, _P]),
     "zkv_pairing4_batch": (C.c_int, [_P, _P, _P, C.c_size_t, _P, _P, _P]),
     "zkv_pairing4_batch_device": (C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, _P, _P]),
+    "zkv_ec_pairing_batch": (C.c_int, [_P, C.c_int, C.c_size_t, _P, _P, _P, C.c_int]),
+    "zkv_ec_pairing": (C.c_int, [_P, C.c_size_t, _P, _P, C.c_int]),
     "zkv_ec_add_batch": (C.c_int, [_P, C.c_size_t, _P, _P, C.c_int]),
     "zkv_ec_mul_batch": (C.c_int, [_P, C.c_size_t, _P, _P, C.c_int]),
     "zkv_g2_mul_batch": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, C.c_int]),

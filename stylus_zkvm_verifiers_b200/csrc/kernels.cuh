@@ -373,17 +373,72 @@ __global__ void __launch_bounds__(LZ_NT, 2) k_miller_lz(int n, MillerArgs a, con
     else if (i0 < n) { g2j* R = rst + i; R->x = lz_ld2(tid + LZ_R * LZ_SLOT); R->y = lz_ld2(tid + (LZ_R + 2) * LZ_SLOT); R->z = lz_ld2(tid + (LZ_R + 4) * LZ_SLOT); }
     if (i0 < n) lz_stg12(fio + i, tid + LZ_F * LZ_SLOT);
 }
-// stages s_lo .. s_hi of the final exponentiation (0..3 = all of it in one launch); st = 6 Fp12 of state per LAUNCHED thread; the last stage writes the status
-__global__ void __launch_bounds__(LZ_NT, 2) k_final_exp_lz(int n, int s_lo, int s_hi, const fp12* in, fp12* st, const uint8_t* flags, uint8_t* status) {
+// stages s_lo .. s_hi of the final exponentiation (0..3 = all of it in one launch); st = 6 Fp12 of state per LAUNCHED thread; the last stage writes the
+// status (pairing_mode: 1 product is one / 0 it is not / 2 the call reverts) and, if gt_out is set, the value (12 x BE-32, zeroed for rejected inputs)
+__global__ void __launch_bounds__(LZ_NT, 2) k_final_exp_lz(int n, int s_lo, int s_hi, const fp12* in, fp12* st, const uint8_t* flags, uint8_t* status, uint8_t* gt_out, int pairing_mode) {
     const int i0 = blockIdx.x * LZ_NT + threadIdx.x, i = i0 < n ? i0 : n - 1;
     for (int s = s_lo; s <= s_hi; s++) lz_final_exp_stage(s, in + i, st + 6 * (size_t)i0);
     if (s_hi < 3 || i0 >= n) return;
     const uint8_t fl = flags[i];
-    if (fl & F_REJECT) { status[i] = reject_status(fl); return; }
+    if (fl & (pairing_mode ? (F_INVALID | F_SELMIS) : F_REJECT)) {
+        status[i] = pairing_mode ? 2 : reject_status(fl);
+        if (gt_out) for (int k = 0; k < 384; k++) gt_out[(size_t)i * 384 + k] = 0;
+        return;
+    }
     const uint32_t tid = lz_tid();
     fp one = fp_one(); uint32_t t = 0;
-    for (int k = 0; k < 12; k++) { fp w = lz_ldfp(tid + (LZ_A + k) * LZ_SLOT); for (int j = 0; j < 8; j++) t |= w.v[j] ^ (k == 0 ? one.v[j] : 0u); }
-    status[i] = t == 0 ? ST_OK : ST_VERIFICATION_FAILED;
+    for (int k = 0; k < 12; k++) {
+        fp w = lz_ldfp(tid + (LZ_A + k) * LZ_SLOT);
+        for (int j = 0; j < 8; j++) t |= w.v[j] ^ (k == 0 ? one.v[j] : 0u);
+        if (gt_out) fp_to_be32(gt_out + (size_t)i * 384 + 32 * k, w);
+    }
+    status[i] = pairing_mode ? (t == 0 ? 1 : 0) : (t == 0 ? ST_OK : ST_VERIFICATION_FAILED);
+}
+// General multi-Miller loop (lz_miller_gen_seg): nvar variable pairs + nfix tabled pairs per instance, pair-major arrays of `in.stride`
+// entries each (stride >= launched threads: surplus threads work on the padding, whose pskip bytes are 1).  iskip[i] != 0: the instance is
+// not evaluated (invalid input): all its pairs are treated as skipped.
+__global__ void __launch_bounds__(LZ_NT, 2) k_pairing_lz(int n, LzGenIn in, fp12* fio, int d_hi, int d_lo, int first, int last) {
+    const size_t i = (size_t)blockIdx.x * LZ_NT + threadIdx.x;
+    const uint32_t tid = lz_tid();
+    if (first) { fp2 z = f2_zero(); lz_st2(tid + LZ_F * LZ_SLOT, f2_one()); for (int k = 1; k < 6; k++) lz_st2(tid + (LZ_F + 2 * k) * LZ_SLOT, z); }
+    else lz_ldg12(tid + LZ_F * LZ_SLOT, fio + i);
+    lz_miller_gen_seg(in, i, d_hi, d_lo, first != 0, last != 0);
+    lz_stg12(fio + i, tid + LZ_F * LZ_SLOT);
+    (void)n;
+}
+// pairing4 service: per-pair skip bytes for k_pairing_lz from the decode flags (pair 0: F_SKIP0, pairs 1..3: 0x20, 0x40, 0x80), the key's own
+// points at infinity (vk_skip) and invalid instances (nothing is evaluated)
+__global__ void k_pairing4_skip(int n, size_t stride, const uint8_t* flags, uint8_t vk_skip, uint8_t* pskip) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t fl = flags[i], bits[4] = {F_SKIP0, 0x20, 0x40, 0x80};
+    const bool bad = (fl & (F_INVALID | F_SELMIS)) != 0;
+    for (int j = 0; j < 4; j++) pskip[(size_t)j * stride + i] = (bad || (fl & bits[j]) || ((vk_skip >> j) & 1)) ? 1 : 0;
+}
+// decode for the general pairing service: one thread per (instance, pair); input record = G1 (64 B) || G2 (128 B) (EIP-197), instance-major
+// in the input, pair-major in the outputs.  pst: 0 usable pair, F_SKIP0 a member is infinity (the pair contributes 1), F_INVALID bad encoding /
+// off curve / off twist (the subgroup test comes after, k_g2_check on the same flags)
+__global__ void k_pairing_decode(int n, int k, size_t stride, const uint8_t* in, fp* px, fp* py, fp2* qx, fp2* qy, uint8_t* pst) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)n * k) return;
+    const size_t i = t / k; const int j = (int)(t % k);
+    const uint8_t* p = in + (i * k + j) * 192;
+    uint32_t rx[8], ry[8];
+    be32_to_raw(rx, p); be32_to_raw(ry, p + 32);
+    fp x, y; int r1 = g1_decode_raw(x, y, rx, ry);
+    fp2 x2, y2; int r2 = g2_decode_bytes(x2, y2, p + 64);
+    const size_t o = (size_t)j * stride + i;
+    px[o] = x; py[o] = y; qx[o] = x2; qy[o] = y2;
+    pst[o] = (r1 == 2 || r2 == 2) ? F_INVALID : (r1 == 1 || r2 == 1) ? F_SKIP0 : 0;
+}
+// per instance: invalid if any pair is; per pair: skip byte for the Miller kernel (every pair of an invalid instance is skipped)
+__global__ void k_pairing_flags(int n, int k, size_t stride, const uint8_t* pst, uint8_t* pskip, uint8_t* iflags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t bad = 0;
+    for (int j = 0; j < k; j++) bad |= pst[(size_t)j * stride + i] & F_INVALID;
+    for (int j = 0; j < k; j++) pskip[(size_t)j * stride + i] = (bad || (pst[(size_t)j * stride + i] & F_SKIP0)) ? 1 : 0;
+    iflags[i] = bad ? F_INVALID : 0;
 }
 // parity hook: one Fp12 tower operation per thread on byte operands (12 x BE-32 each, tower order).
 // op 0: a*b  1: a^2  2: a * line(b.c0.c0, b.c0.c1, b.c0.c2)  3: cyclotomic square  4: 1/a  5..7: Frobenius^(op-4)  8: final exponentiation  9: single-pair Miller loop

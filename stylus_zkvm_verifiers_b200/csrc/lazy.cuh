@@ -266,6 +266,64 @@ LZ_FN2 void lz_miller_norm_seg(LzMillerIn in, int d_hi, int d_lo, bool last) {
         li++;
     }
 }
+// General multi-Miller loop on slots (pairing services): `nvar` pairs with their own variable G2 point, then `nfix` pairs whose G2 points
+// have tabled (unscaled) lines; unscaled line products throughout, so the value is the oracle's Miller value bit for bit.  Arrays are
+// pair-major (pair j of instance i at [j * stride + i]).  With more than one variable pair the accumulators R_j do not fit in the slots:
+// R_j lives in global memory (`rst`, L2-resident) and visits the R slots for its own step; with one variable pair R stays in the slots.
+struct LzGenIn {
+    const fp *px, *py;              // G1 points, (nvar + nfix) x stride
+    const fp2 *qx, *qy;             // variable G2 points, nvar x stride
+    g2j* rst;                       // R_j between steps / segments, nvar x stride
+    const line_t* tabs[3];          // line tables of the fixed G2 points
+    const uint8_t* pskip;           // per pair: != 0 -> the pair contributes 1 (a member at infinity, or an instance that is not evaluated)
+    size_t stride; int nvar, nfix;
+};
+LZ_FN2 void lz_miller_gen_seg(LzGenIn in, size_t i, int d_hi, int d_lo, bool first, bool last) {
+    const uint32_t tid = lz_tid(), F = tid + LZ_F * LZ_SLOT, T = tid + LZ_T * LZ_SLOT, RR = tid + LZ_R * LZ_SLOT, L = tid + LZ_L * LZ_SLOT;
+    const bool keep = in.nvar == 1;        // R stays in the slots for the whole segment
+    int li = 0;
+    for (int d = ZKV_ATE_NAF_LEN - 2; d > d_hi; d--) li += 1 + (C_ATE_NAF[d] != 0);
+    if (keep) {
+        if (first) { lz_st2(RR, in.qx[i]); lz_st2(RR + 2 * LZ_SLOT, in.qy[i]); lz_st2(RR + 4 * LZ_SLOT, f2_one()); }
+        else { const g2j* R = in.rst + i; lz_st2(RR, R->x); lz_st2(RR + 2 * LZ_SLOT, R->y); lz_st2(RR + 4 * LZ_SLOT, R->z); }
+    }
+    const int nsteps = (d_hi - d_lo + 1) + (last ? 2 : 0);
+    for (int step = 0; step < nsteps; step++) {
+        const int d = d_hi - step;                          // d < d_lo: the two Frobenius steps
+        const int frob = d < d_lo ? d_lo - d : 0;           // 1, 2
+        if (!frob && d != ZKV_ATE_NAF_LEN - 2) lz_f12sqr(F, T);
+        const int dg = frob ? 1 : C_ATE_NAF[d];
+        for (int phase = frob ? 1 : 0; phase < 2; phase++) {                // phase 0: doubling lines, phase 1: addition lines (if the digit is non-zero)
+            if (phase == 1 && !dg) break;
+            for (int j = 0; j < in.nvar; j++) {
+                const size_t ij = (size_t)j * in.stride + i;
+                const bool off = in.pskip[ij] != 0;
+                if (!keep) {
+                    if (first && step == 0 && phase == 0) { lz_st2(RR, in.qx[ij]); lz_st2(RR + 2 * LZ_SLOT, in.qy[ij]); lz_st2(RR + 4 * LZ_SLOT, f2_one()); }
+                    else { const g2j* R = in.rst + ij; lz_st2(RR, R->x); lz_st2(RR + 2 * LZ_SLOT, R->y); lz_st2(RR + 4 * LZ_SLOT, R->z); }
+                }
+                fp2 a;
+                if (phase == 0) a = lz_line_dbl(RR, L, in.px + ij, in.py + ij, off);
+                else {
+                    fp2 x = in.qx[ij], y = in.qy[ij];
+                    if (frob) { if (frob == 1) { f2_conj(x, x); f2_conj(y, y); } x = f2v_mul(x, f2_const(frob == 1 ? C_FROB1[2] : C_FROB2[2])); y = f2v_mul(y, f2_const(frob == 1 ? C_FROB1[3] : C_FROB2[3])); if (frob == 2) y = f2v_neg(y); }
+                    else if (dg < 0) y = f2v_neg(y);
+                    a = lz_line_add(RR, L, x, y, in.px + ij, in.py + ij, off);
+                }
+                lz_mul_line(F, T, L, a);
+                if (!keep) { g2j* R = in.rst + ij; R->x = lz_ld2(RR); R->y = lz_ld2(RR + 2 * LZ_SLOT); R->z = lz_ld2(RR + 4 * LZ_SLOT); }
+            }
+            for (int j = 0; j < in.nfix; j++) {
+                const size_t ij = (size_t)(in.nvar + j) * in.stride + i;
+                const line_t ln = in.tabs[j][li];
+                fp2 a = lz_line_out(L, ln.l0, ln.l3, ln.l4, in.px[ij], in.py[ij], in.pskip[ij] != 0);
+                lz_mul_line(F, T, L, a);
+            }
+            li++;
+        }
+    }
+    if (keep && !last) { g2j* R = in.rst + i; R->x = lz_ld2(RR); R->y = lz_ld2(RR + 2 * LZ_SLOT); R->z = lz_ld2(RR + 4 * LZ_SLOT); }
+}
 LZ_INL void lz_miller_init(const fp2& qx, const fp2& qy) {       // f = 1, R = (qx, qy, 1)
     const uint32_t tid = lz_tid();
     fp2 one = f2_one(), z = f2_zero();

@@ -62,7 +62,8 @@ struct DevCtx {
     VkDev h_vk; g1aff h_ic0;
     // workspace
     size_t cap = 0;
-    fp* px[4] = {nullptr, nullptr, nullptr, nullptr}; fp* py[4] = {nullptr, nullptr, nullptr, nullptr};
+    fp* px[4] = {nullptr, nullptr, nullptr, nullptr}; fp* py[4] = {nullptr, nullptr, nullptr, nullptr};   // four slices of ONE allocation each, `stride` entries apart (pair-major: the general Miller kernel indexes [j * stride + i])
+    size_t stride = 0; uint8_t* pskip = nullptr;                                                          // pairing service: per-pair skip bytes, 4 x stride
     fp2 *qx = nullptr, *qy = nullptr; fp12* f = nullptr; g2j* rst = nullptr; fp* sl = nullptr; fp12* fes = nullptr; size_t fes_cap = 0; uint8_t *flags = nullptr, *status = nullptr; uint32_t* scal = nullptr; size_t scal_words = 0;
     // staging
     uint8_t* d_in = nullptr; size_t d_in_cap = 0; uint8_t* d_out = nullptr; size_t d_out_cap = 0;
@@ -92,12 +93,17 @@ struct Tuning {
 static constexpr size_t PAD = 256;          // workspace slack behind a batch: surplus threads of the last block park their state there
 static int ctx_reserve(DevCtx* c, size_t n, size_t scal_words_per_proof) {
     if (n > c->cap) {
-        for (int j = 0; j < 4; j++) { cudaFree(c->px[j]); cudaFree(c->py[j]); }
+        cudaFree(c->px[0]); cudaFree(c->py[0]); cudaFree(c->pskip);
         cudaFree(c->qx); cudaFree(c->qy); cudaFree(c->f); cudaFree(c->flags); cudaFree(c->status); cudaFree(c->rst); cudaFree(c->sl);
         c->cap = 0;
-        for (int j = 0; j < 4; j++) { CK(cudaMalloc(&c->px[j], n * sizeof(fp))); CK(cudaMalloc(&c->py[j], n * sizeof(fp))); }
-        CK(cudaMalloc(&c->qx, n * sizeof(fp2))); CK(cudaMalloc(&c->qy, n * sizeof(fp2))); CK(cudaMalloc(&c->f, n * sizeof(fp12)));
-        CK(cudaMalloc(&c->rst, n * sizeof(g2j))); CK(cudaMalloc(&c->sl, (n + PAD) * 4 * sizeof(fp)));
+        const size_t st = n + PAD;
+        CK(cudaMalloc(&c->px[0], 4 * st * sizeof(fp))); CK(cudaMalloc(&c->py[0], 4 * st * sizeof(fp))); CK(cudaMalloc(&c->pskip, 4 * st));
+        CK(cudaMemset(c->px[0], 0, 4 * st * sizeof(fp))); CK(cudaMemset(c->py[0], 0, 4 * st * sizeof(fp))); CK(cudaMemset(c->pskip, 1, 4 * st));
+        for (int j = 1; j < 4; j++) { c->px[j] = c->px[0] + j * st; c->py[j] = c->py[0] + j * st; }
+        c->stride = st;
+        CK(cudaMalloc(&c->qx, st * sizeof(fp2))); CK(cudaMalloc(&c->qy, st * sizeof(fp2))); CK(cudaMalloc(&c->f, st * sizeof(fp12)));
+        CK(cudaMemset(c->qx, 0, st * sizeof(fp2))); CK(cudaMemset(c->qy, 0, st * sizeof(fp2)));
+        CK(cudaMalloc(&c->rst, st * sizeof(g2j))); CK(cudaMalloc(&c->sl, st * 4 * sizeof(fp)));
         CK(cudaMalloc(&c->flags, n)); CK(cudaMalloc(&c->status, n));
         c->cap = n;
     }
@@ -122,7 +128,7 @@ static int ctx_release_async(DevCtx* c, cudaStream_t s) { CK(cudaEventRecord(c->
 static void ctx_free(DevCtx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    for (int j = 0; j < 4; j++) { cudaFree(c->px[j]); cudaFree(c->py[j]); }
+    cudaFree(c->px[0]); cudaFree(c->py[0]); cudaFree(c->pskip);
     cudaFree(c->qx); cudaFree(c->qy); cudaFree(c->f); cudaFree(c->flags); cudaFree(c->status); cudaFree(c->scal); cudaFree(c->rst); cudaFree(c->sl); cudaFree(c->fes);
     cudaFree(c->d_in); cudaFree(c->d_out); cudaFreeHost(c->h_pin); cudaFreeHost(c->h_out);
     cudaFree(c->d_vk); cudaFree(c->d_lines); cudaFree(c->d_nlines); cudaFree(c->d_pre); cudaFree(c->d_tab); cudaFree(c->d_ic0);
@@ -156,6 +162,7 @@ static int vk_build_on(zkv_vk* vk, DevCtx* c) {
     for (auto& e : c->ev_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CK(cudaFuncSetAttribute(k_miller_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_final_exp_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_pairing_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_BYTES));
     int nt = vk->n_ic - 1;
     CK(cudaMalloc(&c->d_vk, sizeof(VkDev))); CK(cudaMalloc(&c->d_lines, sizeof(line_t) * 3 * ZKV_LINES_PER_G2)); CK(cudaMalloc(&c->d_nlines, sizeof(nline_t) * 2 * ZKV_LINES_PER_G2)); CK(cudaMalloc(&c->d_pre, sizeof(fp12)));
     CK(cudaMalloc(&c->d_tab, sizeof(g1aff) * (size_t)nt * ZKV_WIN_PER_SCALAR * ZKV_WIN_ENTRIES)); CK(cudaMalloc(&c->d_ic0, sizeof(g1aff)));
@@ -319,8 +326,8 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
     else k_miller<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, a, flags, c->f + o);
     if (timed) CK(cudaEventRecord(c->ev[4], s));
     if (vk->tune.layout.load()) {
-        if (stages && !timed) { for (int st = 0; st < 4; st++) k_final_exp_lz<<<nblk(m, LZ_NT), LZ_NT, LZ_SMEM_BYTES, s>>>(m, st, st, c->f + o, c->fes + 6 * o, flags, j.d_status + jo); nl += 3; }
-        else k_final_exp_lz<<<nblk(m, LZ_NT), LZ_NT, LZ_SMEM_BYTES, s>>>(m, 0, 3, c->f + o, c->fes + 6 * o, flags, j.d_status + jo);
+        if (stages && !timed) { for (int st = 0; st < 4; st++) k_final_exp_lz<<<nblk(m, LZ_NT), LZ_NT, LZ_SMEM_BYTES, s>>>(m, st, st, c->f + o, c->fes + 6 * o, flags, j.d_status + jo, nullptr, 0); nl += 3; }
+        else k_final_exp_lz<<<nblk(m, LZ_NT), LZ_NT, LZ_SMEM_BYTES, s>>>(m, 0, 3, c->f + o, c->fes + 6 * o, flags, j.d_status + jo, nullptr, 0);
     } else if (stages && !timed) {
         for (int st = 0; st < 4; st++) k_final_exp_stage<<<nblk(m, ZKV_HTPB_FE), ZKV_HTPB_FE, 0, s>>>(m, st, c->f + o, c->fes + 5 * o, flags, j.d_status + jo);
         nl += 3;
@@ -706,10 +713,18 @@ static int pairing4_chain(DevCtx* c, const zkv_vk* vk, size_t o, int n, const ui
     a.nfixed = 3; a.pre = nullptr;
     a.skip_bit[0] = F_SKIP0; a.skip_bit[1] = 0x20; a.skip_bit[2] = 0x40; a.skip_bit[3] = 0x80;
     a.vk_skip = (uint8_t)((c->h_vk.g2_inf[0] ? 2 : 0) | (c->h_vk.g2_inf[1] ? 4 : 0) | (c->h_vk.g2_inf[2] ? 8 : 0));
-    k_miller<<<nblk(n, ZKV_HTPB), ZKV_HTPB, 0, s>>>(n, a, flags, c->f + o);
+    const bool lazy = vk->tune.layout.load() != 0;
+    if (lazy) {                 // shared-memory-resident general Miller loop: one variable pair + the three tabled key points, unscaled lines (the oracle's Miller value)
+        k_pairing4_skip<<<nblk(n), TPB, 0, s>>>(n, c->stride, flags, a.vk_skip, c->pskip + o);
+        LzGenIn gi; memset(&gi, 0, sizeof gi);
+        gi.px = c->px[0] + o; gi.py = c->py[0] + o; gi.qx = c->qx + o; gi.qy = c->qy + o; gi.rst = c->rst + o; gi.pskip = c->pskip + o; gi.stride = c->stride; gi.nvar = 1; gi.nfix = 3;
+        for (int j = 0; j < 3; j++) gi.tabs[j] = a.tabs[j];
+        k_pairing_lz<<<nblk(n, LZ_NT), LZ_NT, LZ_SMEM_BYTES, s>>>(n, gi, c->f + o, ZKV_ATE_NAF_LEN - 2, 0, 1, 1);
+    } else k_miller<<<nblk(n, ZKV_HTPB), ZKV_HTPB, 0, s>>>(n, a, flags, c->f + o);
     if (timed) CK(cudaEventRecord(c->ev[4], s));
     if (d_miller) k_f12_to_bytes<<<nblk(n), TPB, 0, s>>>(n, c->f + o, d_miller + o * 384);
-    k_final_exp<<<nblk(n, ZKV_HTPB_FE), ZKV_HTPB_FE, 0, s>>>(n, c->f + o, flags, d_ok + o, d_gt ? d_gt + o * 384 : nullptr, 1);
+    if (lazy) k_final_exp_lz<<<nblk(n, LZ_NT), LZ_NT, LZ_SMEM_BYTES, s>>>(n, 0, 3, c->f + o, c->fes + 6 * o, flags, d_ok + o, d_gt ? d_gt + o * 384 : nullptr, 1);
+    else k_final_exp<<<nblk(n, ZKV_HTPB_FE), ZKV_HTPB_FE, 0, s>>>(n, c->f + o, flags, d_ok + o, d_gt ? d_gt + o * 384 : nullptr, 1);
     if (timed) CK(cudaEventRecord(c->ev[5], s));
     CK(cudaGetLastError());
     return 0;
@@ -856,6 +871,71 @@ extern "C" int zkv_g2_mul_batch(const uint8_t* points, int broadcast_point, cons
     return with_scratch(device, points, broadcast_point ? 128 : n * 128, scalars, n * 32, out, n * 128, reverted, n,
                         [&](uint8_t* d0, uint8_t* d1, uint8_t* o0, uint8_t* o1) { k_g2_mul<<<nblk(n), TPB>>>((int)n, d0, broadcast_point, d1, o0, o1); });
 }
+// ------------------------------------------------------------------------------------------ general ecPairing service (0x08, groth16.rs:109-128)
+// n instances of a k-pair product check with EVERY G2 point variable: the byte semantics of the precompile (EIP-197): each pair is
+// G1 (64 B) || G2 (128 B); a coordinate >= p, a point off its curve or a G2 point outside the order-r subgroup makes the call fail
+// (reverted[i] = 1, out word zero); a pair with a member at infinity contributes 1; k = 0 is the empty product (true).
+// out: n x 32 B, the precompile's return word (0...01 or 0...00); miller_out (optional, n x 384 B): the Miller-loop value.
+static int ec_pairing_on(int device, const uint8_t* in, int k, size_t n, uint8_t* out, uint8_t* reverted, uint8_t* miller_out) {
+    CK(cudaSetDevice(device));
+    CK(cudaFuncSetAttribute(k_pairing_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_final_exp_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_BYTES));
+    const size_t CH = (size_t)1 << 16;
+    const size_t cap = std::min(CH, (n + LZ_NT - 1) / LZ_NT * LZ_NT), K = (size_t)k;
+    uint8_t *d_in = nullptr, *d_pst = nullptr, *d_pskip = nullptr, *d_ifl = nullptr, *d_st = nullptr, *d_ml = nullptr;
+    fp *d_px = nullptr, *d_py = nullptr; fp2 *d_qx = nullptr, *d_qy = nullptr; g2j* d_r = nullptr; fp12 *d_f = nullptr, *d_fes = nullptr;
+    auto release = [&]() { cudaFree(d_in); cudaFree(d_pst); cudaFree(d_pskip); cudaFree(d_ifl); cudaFree(d_st); cudaFree(d_ml); cudaFree(d_px); cudaFree(d_py); cudaFree(d_qx); cudaFree(d_qy); cudaFree(d_r); cudaFree(d_f); cudaFree(d_fes); };
+#define CKR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { release(); return fail(ZKV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    CKR(cudaMalloc(&d_in, cap * K * 192)); CKR(cudaMalloc(&d_pst, cap * K)); CKR(cudaMalloc(&d_pskip, cap * K)); CKR(cudaMalloc(&d_ifl, cap)); CKR(cudaMalloc(&d_st, cap));
+    CKR(cudaMalloc(&d_px, cap * K * sizeof(fp))); CKR(cudaMalloc(&d_py, cap * K * sizeof(fp))); CKR(cudaMalloc(&d_qx, cap * K * sizeof(fp2))); CKR(cudaMalloc(&d_qy, cap * K * sizeof(fp2)));
+    CKR(cudaMalloc(&d_r, cap * K * sizeof(g2j))); CKR(cudaMalloc(&d_f, cap * sizeof(fp12))); CKR(cudaMalloc(&d_fes, cap * 6 * sizeof(fp12)));
+    if (miller_out) CKR(cudaMalloc(&d_ml, cap * 384));
+    std::vector<uint8_t> h_st(cap), h_ifl(cap);
+    for (size_t s0 = 0; s0 < n; s0 += CH) {
+        const size_t m = std::min(CH, n - s0);
+        const int blocks = nblk(m, LZ_NT);
+        CKR(cudaMemcpy(d_in, in + s0 * K * 192, m * K * 192, cudaMemcpyHostToDevice));
+        CKR(cudaMemset(d_px, 0, cap * K * sizeof(fp))); CKR(cudaMemset(d_py, 0, cap * K * sizeof(fp))); CKR(cudaMemset(d_qx, 0, cap * K * sizeof(fp2))); CKR(cudaMemset(d_qy, 0, cap * K * sizeof(fp2)));
+        CKR(cudaMemset(d_pst, F_SKIP0, cap * K)); CKR(cudaMemset(d_pskip, 1, cap * K));          // padding entries: skipped pairs
+        k_pairing_decode<<<nblk(m * K), TPB>>>((int)m, k, cap, d_in, d_px, d_py, d_qx, d_qy, d_pst);
+        k_g2_check<<<nblk(cap * K), TPB>>>((int)(cap * K), d_qx, d_qy, d_pst);
+        k_pairing_flags<<<nblk(m), TPB>>>((int)m, k, cap, d_pst, d_pskip, d_ifl);
+        LzGenIn gi; memset(&gi, 0, sizeof gi);
+        gi.px = d_px; gi.py = d_py; gi.qx = d_qx; gi.qy = d_qy; gi.rst = d_r; gi.pskip = d_pskip; gi.stride = cap; gi.nvar = k; gi.nfix = 0;
+        k_pairing_lz<<<blocks, LZ_NT, LZ_SMEM_BYTES>>>((int)m, gi, d_f, ZKV_ATE_NAF_LEN - 2, 0, 1, 1);
+        if (miller_out) k_f12_to_bytes<<<nblk(m), TPB>>>((int)m, d_f, d_ml);
+        k_final_exp_lz<<<blocks, LZ_NT, LZ_SMEM_BYTES>>>((int)m, 0, 3, d_f, d_fes, d_ifl, d_st, nullptr, 1);
+        CKR(cudaGetLastError());
+        CKR(cudaMemcpy(h_st.data(), d_st, m, cudaMemcpyDeviceToHost)); CKR(cudaMemcpy(h_ifl.data(), d_ifl, m, cudaMemcpyDeviceToHost));
+        if (miller_out) CKR(cudaMemcpy(miller_out + s0 * 384, d_ml, m * 384, cudaMemcpyDeviceToHost));
+        for (size_t t = 0; t < m; t++) {
+            uint8_t* o = out + (s0 + t) * 32; memset(o, 0, 32);
+            if (h_ifl[t]) { reverted[s0 + t] = 1; if (miller_out) memset(miller_out + (s0 + t) * 384, 0, 384); }
+            else { reverted[s0 + t] = 0; o[31] = h_st[t] == 1 ? 1 : 0; }
+        }
+    }
+#undef CKR
+    release();
+    return 0;
+}
+extern "C" int zkv_ec_pairing_batch(const uint8_t* in, int k, size_t n, uint8_t* out, uint8_t* reverted, uint8_t* miller_out, int device) {
+    if (!out || !reverted || k < 0 || k > 64 || (k && n && !in)) return fail(ZKV_ERR_ARG, "zkv_ec_pairing_batch: bad argument");
+    if (n == 0) return 0;
+    if (zkv_device_count() <= device || device < 0) return fail(ZKV_ERR_CUDA, "no such CUDA device (this library has no CPU path)");
+    if (k == 0) {                                           // empty product: true, no curve work at all (EIP-197)
+        for (size_t i = 0; i < n; i++) { memset(out + 32 * i, 0, 32); out[32 * i + 31] = 1; reverted[i] = 0; }
+        if (miller_out) for (size_t i = 0; i < n; i++) { memset(miller_out + 384 * i, 0, 384); miller_out[384 * i + 31] = 1; }
+        return 0;
+    }
+    return ec_pairing_on(device, in, k, n, out, reverted, miller_out);
+}
+// one precompile call on raw bytes: len must be a multiple of 192 (else the call fails: *reverted = 1)
+extern "C" int zkv_ec_pairing(const uint8_t* in, size_t len, uint8_t out[32], uint8_t* reverted, int device) {
+    if (!out || !reverted || (len && !in)) return fail(ZKV_ERR_ARG, "zkv_ec_pairing: null argument");
+    if (len % 192) { memset(out, 0, 32); *reverted = 1; return 0; }
+    return zkv_ec_pairing_batch(in, (int)(len / 192), 1, out, reverted, nullptr, device);
+}
+
 extern "C" int zkv_last_stage_ms(const void* handle_vk, int device, float* out, int cap) {
     const zkv_vk* vk = (const zkv_vk*)handle_vk;
     if (!vk || !out) return fail(ZKV_ERR_ARG, "null");

@@ -320,6 +320,21 @@ def vk_x_batch(vk, signals, k, n):
     return out
 
 
+def ec_pairing_batch(data, k, n, want_miller=False, device=0):
+    """Precompile 0x08 on n instances of k pairs (every G2 variable): returns (words n x 32 uint8, reverted n uint8[, miller n x 384])."""
+    out = np.zeros(n * 32, dtype=np.uint8); rev = np.zeros(n, dtype=np.uint8)
+    ml = np.zeros(n * 384, dtype=np.uint8) if want_miller else None
+    N.check(N.lib().zkv_ec_pairing_batch(N.buf(data) if (k and n) else None, k, n, out.ctypes.data, rev.ctypes.data, ml.ctypes.data if want_miller else None, device))
+    return (out, rev, ml) if want_miller else (out, rev)
+
+
+def ec_pairing(data, device=0):
+    """One precompile 0x08 call on raw bytes: the 32-byte return word, or None if the call fails (what the reference sees as a revert)."""
+    out = C.create_string_buffer(32); rev = C.c_uint8(0)
+    N.check(N.lib().zkv_ec_pairing(data or None, len(data), out, C.byref(rev), device))
+    return None if rev.value else out.raw
+
+
 def fp_mul_batch(a, b, n, device=0):
     out = np.zeros(n * 32, dtype=np.uint8)
     N.check(N.lib().zkv_fp_mul_batch(N.buf(a), N.buf(b), n, out.ctypes.data, device))

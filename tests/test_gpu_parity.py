@@ -517,3 +517,57 @@ def test_concurrent_calls_on_shared_and_separate_handles(Z, gpu, fx):
     [t.start() for t in th]; [t.join() for t in th]
     assert not errs, errs
     assert all(0 < int((w == 0).sum()) < len(w) for _, w in jobs)
+
+
+def test_general_ec_pairing_service_vs_oracle(Z, gpu):
+    """zkv_ec_pairing_batch / zkv_ec_pairing: precompile 0x08 with every G2 point variable (the seam groth16.rs:109-128 calls), k = 0..6
+    pairs, against the oracle's zkvo_ec_pairing: return word, failure (revert) and the Miller-loop value bit for bit; products that are
+    one by bilinearity, members at infinity, points off the curve / twist, coordinates >= p, G2 points outside the subgroup, bad lengths."""
+    from stylus_zkvm_verifiers_b200 import synth as S
+    rng = S.SplitMix64(0xB2000041)
+    G1, G2 = S.G1_GEN, S.G2_GEN
+    neg = lambda p: p[:32] + O.w32((P - int.from_bytes(p[32:], "big")) % P)
+    wrong = S.random_twist_point(rng)
+
+    def pairs(k, kind):
+        """k pairs; kind: 'one' product is 1 by construction, 'rand' random, plus mutations"""
+        ps = []
+        if kind == "one" and k >= 2:
+            tot = 0
+            for j in range(k - 1):
+                a, b = rng.fr(), rng.fr(); tot = (tot + a * b) % R
+                ps.append(O.g1_mul(G1, a) + O.g2_mul(G2, b))
+            ps.append(neg(O.g1_mul(G1, tot)) + G2)
+        else:
+            ps = [O.g1_mul(G1, rng.fr()) + O.g2_mul(G2, rng.fr()) for _ in range(k)]
+        return ps
+    for k in range(0, 7):
+        n = 24
+        inst = []
+        for i in range(n):
+            ps = pairs(k, "one" if i % 2 == 0 else "rand")
+            if k:
+                j = rng.below(k)
+                m = i % 12
+                if m == 3: ps[j] = bytes(64) + ps[j][64:]                       # G1 at infinity: the pair contributes 1
+                elif m == 5: ps[j] = ps[j][:64] + bytes(128)                    # G2 at infinity
+                elif m == 7: ps[j] = O.w32(1) + O.w32(3) + ps[j][64:]           # G1 off the curve -> the call fails
+                elif m == 9: ps[j] = ps[j][:64] + wrong                         # G2 on the twist, outside the subgroup -> fails
+                elif m == 10: ps[j] = ps[j][:64] + O.w32(P) + ps[j][96:]        # coordinate >= p -> fails
+                elif m == 11: b = bytearray(ps[j]); b[191] ^= 1; ps[j] = bytes(b)   # G2 off the twist -> fails
+            inst.append(b"".join(ps))
+        words, rev, ml = Z.ec_pairing_batch(b"".join(inst), k, n, want_miller=True)
+        for i in range(n):
+            ret = O.ec_pairing(inst[i], debug=True) if k else (O.ec_pairing(b""), None, None)
+            want = ret[0] if isinstance(ret, tuple) else ret
+            if want is None:
+                assert rev[i] == 1 and not words[32 * i:32 * i + 32].any(), (k, i)
+            else:
+                assert rev[i] == 0 and bytes(words[32 * i:32 * i + 32]) == want, (k, i)
+                if k:
+                    assert bytes(ml[384 * i:384 * i + 384]) == ret[1], (k, i, "Miller value")
+        if k >= 2:
+            assert any(bytes(words[32 * i:32 * i + 32])[31] == 1 for i in range(n)) and any(rev)
+    one = O.w32(1)
+    assert Z.ec_pairing(b"") == one and Z.ec_pairing(G1 + bytes(128)) == one and Z.ec_pairing(G1 + G2) == O.w32(0)
+    assert Z.ec_pairing((G1 + G2)[:-1]) is None and Z.ec_pairing(G1 + G2 + neg(G1) + G2) == one

@@ -161,3 +161,54 @@ def test_python_referee_agrees(fx):
     Q = B._dec_g2(data[64:])
     e = B.final_exp(B.miller((1, 2), Q))
     assert B.tower_to_poly(gt_t) == B.f12pow(e, B.LAMBDA)
+
+
+@pytest.mark.timeout(900)
+def test_python_referee_agrees_on_every_mutation_class(fx):
+    """the independent Python referee (affine arithmetic, different Fp12 basis, plain-pow final exponentiation, its own
+    restatement of the verifiers' front checks) and the C oracle must return the same status for >= 3 samples of EVERY class of the
+    config-4 mix (valid, tampered, off-curve, coordinate >= p incl. the (0, Q) quirk, wrong-subgroup G2, infinity members, malformed),
+    for both proof shapes: the reject side of the oracle is pinned by a second implementation family, not only the accept side."""
+    import bn254_py as B
+    from stylus_zkvm_verifiers_b200 import synth as S
+
+    class OB:
+        def g1_mul(self, sc): return [O.g1_mul(S.G1_GEN, s) for s in sc]
+        def g2_mul(self, sc): return [O.g2_mul(S.G2_GEN, s) for s in sc]
+    be = lambda b: int.from_bytes(b, "big")
+    g1 = lambda b: (be(b[:32]), be(b[32:64]))
+    g2 = lambda b: ((be(b[0:32]), be(b[32:64])), (be(b[64:96]), be(b[96:128])))
+    pyvk = lambda vk: {"alpha": g1(vk.alpha), "beta": g2(vk.beta), "gamma": g2(vk.gamma), "delta": g2(vk.delta), "ic": [g1(p) for p in vk.ic]}
+    want_classes = [c for c, _ in S.MIXED_CLASSES]
+    seen = {}
+    # RISC Zero shape
+    vk = S.make_vk(OB(), 0, 6, 0xB2000031)
+    ro = O.Risc0Oracle(O.Vk(0, vk.alpha, vk.beta, vk.gamma, vk.delta, vk.ic)); ro.initialize(fx["control_root"], fx["bn254_control_id"])
+    assert B.risc0_selector(fx["control_root"], fx["bn254_control_id"], pyvk(vk)) == ro.selector()
+    b = S.make_risc0_batch(OB(), vk, ro.selector(), fx["control_root"], fx["bn254_control_id"], fx["sys0"], 160, 0xB2000032, pool=16)
+    S.mutate_risc0(b, OB(), S.SplitMix64(0xB2000033))
+    want = ro.verify_batch(b.seals, b.image_ids, b.journals)
+    pick = []
+    for i, c in enumerate(b.classes):
+        if seen.get(("risc0", c), 0) < 3:
+            seen[("risc0", c)] = seen.get(("risc0", c), 0) + 1; pick.append(i)
+    pv = pyvk(vk)
+    for i in pick:
+        got = B.risc0_verify_status(pv, ro.selector(), fx["control_root"], fx["bn254_control_id"], b.seals[i], b.image_ids[i], b.journals[i])
+        assert got == int(want[i]), ("risc0", b.classes[i], i, got, int(want[i]))
+    # SP1 shape
+    vk = S.make_vk(OB(), 1, 3, 0xB2000034)
+    sb = S.make_sp1_batch(OB(), vk, 160, 0xB2000035, pool=16)
+    S.mutate_sp1(sb, OB(), S.SplitMix64(0xB2000036))
+    want = O.sp1_verify_batch(O.Vk(1, vk.alpha, vk.beta, vk.gamma, vk.delta, vk.ic), S.SP1_SELECTOR, sb.vkeys, sb.public_values, sb.proofs)
+    pick = []
+    for i, c in enumerate(sb.classes):
+        if seen.get(("sp1", c), 0) < 3:
+            seen[("sp1", c)] = seen.get(("sp1", c), 0) + 1; pick.append(i)
+    pv = pyvk(vk)
+    for i in pick:
+        got = B.sp1_verify_status(pv, S.SP1_SELECTOR, sb.vkeys[i], sb.public_values[i], sb.proofs[i])
+        assert got == int(want[i]), ("sp1", sb.classes[i], i, got, int(want[i]))
+    for shape in ("risc0", "sp1"):
+        for c in want_classes:
+            assert seen.get((shape, c), 0) >= 3, (shape, c, seen)
