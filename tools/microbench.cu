@@ -1,3 +1,7 @@
+// (round 2: the loop-invariant mad.wide kernels of round 1 were removed - ptxas strength-reduces them to 64-bit adds, so their
+// figures were IADD3 rates; the 9x9 / immediate / constant-bank / register-operand mad.wide kernels went the same way in round 2: all but
+// one multiplicand were loop invariant, so nvcc hoisted the products out of the loop.  Every kernel left here has its multiplies INSIDE
+// the timed loop in the SASS (cuobjdump -sass: k_chain 320 IMAD.WIDE.U32[.X] per iteration, k_asm_*: data-dependent multiplicands).)
 // K0 microbenchmarks: issue rates of the integer instructions the Fp multiplier is built from,
 // measured on the box the kernels run on.  Prints one JSON object.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench.bin tools/microbench.cu
 #include <cstdint>
@@ -5,17 +9,6 @@
 #include <cuda_runtime.h>
 
 #define REP8(x) x x x x x x x x
-// 8 independent mad.wide.u32 accumulators, no carries
-__global__ void k_wide(uint64_t* out, uint32_t a0, uint32_t b0, int iters) {
-    uint32_t a = a0 + threadIdx.x, b = b0 ^ blockIdx.x;
-    uint64_t c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8;
-    for (int k = 0; k < iters; k++) {
-        REP8(asm volatile("mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\tmad.wide.u32 %2, %8, %9, %2;\n\tmad.wide.u32 %3, %8, %9, %3;\n\t"
-                          "mad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\tmad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
-                          : "+l"(c0), "+l"(c1), "+l"(c2), "+l"(c3), "+l"(c4), "+l"(c5), "+l"(c6), "+l"(c7) : "r"(a), "r"(b));)
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
-}
 // carry chains: two independent 8-limb accumulators, each updated by a 4-product chain (mad.lo.cc / madc.hi.cc), as one row of the multiplier
 __global__ void k_chain(uint32_t* out, uint32_t a0, uint32_t b0, int iters) {
     uint32_t a1 = a0 + threadIdx.x, a2 = a1 * 3, a3 = a1 * 5, a4 = a1 * 7, b = b0 ^ blockIdx.x;
@@ -29,17 +22,6 @@ __global__ void k_chain(uint32_t* out, uint32_t a0, uint32_t b0, int iters) {
                           : "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(b));)
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = e0 ^ e1 ^ e2 ^ e3 ^ e4 ^ e5 ^ e6 ^ e7 ^ o0 ^ o1 ^ o2 ^ o3 ^ o4 ^ o5 ^ o6 ^ o7;
-}
-// same 8 products per group but without carries: distinct multiplicands, 8 independent 64-bit accumulators
-__global__ void k_wide_distinct(uint64_t* out, uint32_t a0, uint32_t b0, int iters) {
-    uint32_t a1 = a0 + threadIdx.x, a2 = a1 * 3, a3 = a1 * 5, a4 = a1 * 7, b = b0 ^ blockIdx.x;
-    uint64_t c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8;
-    for (int k = 0; k < iters; k++) {
-        REP8(asm volatile("mad.wide.u32 %0, %8, %12, %0;\n\tmad.wide.u32 %1, %9, %12, %1;\n\tmad.wide.u32 %2, %10, %12, %2;\n\tmad.wide.u32 %3, %11, %12, %3;\n\t"
-                          "mad.wide.u32 %4, %9, %12, %4;\n\tmad.wide.u32 %5, %10, %12, %5;\n\tmad.wide.u32 %6, %11, %12, %6;\n\tmad.wide.u32 %7, %8, %12, %7;"
-                          : "+l"(c0), "+l"(c1), "+l"(c2), "+l"(c3), "+l"(c4), "+l"(c5), "+l"(c6), "+l"(c7) : "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(b));)
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
 }
 // plain 32-bit IMAD (lo)
 __global__ void k_imad(uint32_t* out, uint32_t a0, uint32_t b0, int iters) {
@@ -77,116 +59,7 @@ __global__ void k_dfma(double* out, double a0, double b0, int iters) {
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7;
 }
-// interleaved DFMA + IMAD.WIDE: do the two pipes overlap?
-__global__ void k_dfma_wide(double* out, double a0, double b0, uint32_t ia, uint32_t ib, int iters) {
-    double a = a0 + threadIdx.x, b = b0 + blockIdx.x;
-    uint32_t x = ia + threadIdx.x, y = ib ^ blockIdx.x;
-    double c0 = 1, c1 = 2, c2 = 3, c3 = 4;
-    uint64_t d0 = 1, d1 = 2, d2 = 3, d3 = 4;
-    for (int k = 0; k < iters; k++) {
-        REP8(asm volatile("fma.rn.f64 %0, %8, %9, %0;\n\tmad.wide.u32 %4, %10, %11, %4;\n\tfma.rn.f64 %1, %8, %9, %1;\n\tmad.wide.u32 %5, %10, %11, %5;\n\t"
-                          "fma.rn.f64 %2, %8, %9, %2;\n\tmad.wide.u32 %6, %10, %11, %6;\n\tfma.rn.f64 %3, %8, %9, %3;\n\tmad.wide.u32 %7, %10, %11, %7;"
-                          : "+d"(c0), "+d"(c1), "+d"(c2), "+d"(c3), "+l"(d0), "+l"(d1), "+l"(d2), "+l"(d3) : "d"(a), "d"(b), "r"(x), "r"(y));)
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = c0 + c1 + c2 + c3 + (double)(d0 ^ d1 ^ d2 ^ d3);
-}
-// IMAD.WIDE interleaved with independent ALU work (IADD3): do ALU instructions ride along for free?
-__global__ void k_wide_alu(uint64_t* out, uint32_t a0, uint32_t b0, int iters) {
-    uint32_t a = a0 + threadIdx.x, b = b0 ^ blockIdx.x;
-    uint64_t c0 = 1, c1 = 2, c2 = 3, c3 = 4;
-    uint32_t s0 = 5, s1 = 6, s2 = 7, s3 = 8;
-    for (int k = 0; k < iters; k++) {
-        REP8(asm volatile("mad.wide.u32 %0, %8, %9, %0;\n\tadd.u32 %4, %4, %8;\n\tmad.wide.u32 %1, %8, %9, %1;\n\txor.b32 %5, %5, %9;\n\t"
-                          "mad.wide.u32 %2, %8, %9, %2;\n\tadd.u32 %6, %6, %9;\n\tmad.wide.u32 %3, %8, %9, %3;\n\tshf.l.wrap.b32 %7, %7, %7, 3;"
-                          : "+l"(c0), "+l"(c1), "+l"(c2), "+l"(c3), "+r"(s0), "+r"(s1), "+r"(s2), "+r"(s3) : "r"(a), "r"(b));)
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ s0 ^ s1 ^ s2 ^ s3;
-}
 
-// signed mad.wide.s32, 9 independent columns x 9 rows with all-distinct multiplicands (the operand pattern of the 29-bit-limb multiplier)
-__global__ void k_swide_9x9(int64_t* out, int32_t a0, int32_t b0, int iters) {
-    int32_t a[9], b[9];
-    for (int i = 0; i < 9; i++) { a[i] = a0 * (i + 1) + threadIdx.x; b[i] = b0 * (i + 3) - blockIdx.x; }
-    int64_t t[17];
-    for (int i = 0; i < 17; i++) t[i] = i;
-    for (int k = 0; k < iters; k++) {
-#pragma unroll
-        for (int i = 0; i < 9; i++)
-#pragma unroll
-            for (int j = 0; j < 9; j++) t[i + j] += (int64_t)a[i] * b[j];
-        a[0] ^= (int32_t)t[8];      // keep the loop from being hoisted
-    }
-    int64_t x = 0;
-    for (int i = 0; i < 17; i++) x ^= t[i];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
-}
-// same, unsigned
-__global__ void k_uwide_9x9(uint64_t* out, uint32_t a0, uint32_t b0, int iters) {
-    uint32_t a[9], b[9];
-    for (int i = 0; i < 9; i++) { a[i] = a0 * (i + 1) + threadIdx.x; b[i] = b0 * (i + 3) - blockIdx.x; }
-    uint64_t t[17];
-    for (int i = 0; i < 17; i++) t[i] = i;
-    for (int k = 0; k < iters; k++) {
-#pragma unroll
-        for (int i = 0; i < 9; i++)
-#pragma unroll
-            for (int j = 0; j < 9; j++) t[i + j] += (uint64_t)a[i] * b[j];
-        a[0] ^= (uint32_t)t[8];
-    }
-    uint64_t x = 0;
-    for (int i = 0; i < 17; i++) x ^= t[i];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
-}
-// unsigned products by the limbs of p as IMMEDIATES (how the reduction rows compile when p is a literal): 8 independent columns
-__global__ void k_uwide_imm(uint64_t* out, uint32_t a0, int iters) {
-    uint32_t m[8];
-    for (int r = 0; r < 8; r++) m[r] = (uint32_t)out[r + (threadIdx.x & 1)] | 0x1000000u;
-    uint64_t t[8];
-    for (int i = 0; i < 8; i++) t[i] = i;
-    for (int k = 0; k < iters; k++) {
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            t[0] += (uint64_t)m[r] * 0x187cfd47u; t[1] += (uint64_t)m[r] * 0x010460b6u; t[2] += (uint64_t)m[r] * 0x1c72a34fu; t[3] += (uint64_t)m[r] * 0x02d522d0u;
-            t[4] += (uint64_t)m[r] * 0x1585d978u; t[5] += (uint64_t)m[r] * 0x02db40c0u; t[6] += (uint64_t)m[r] * 0x00a6e141u; t[7] += (uint64_t)m[r] * 0x0e5c2634u;
-        }
-    }
-    uint64_t x = 0;
-    for (int i = 0; i < 8; i++) x ^= t[i];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
-}
-__constant__ uint32_t CP[9] = {0x187cfd47u, 0x010460b6u, 0x1c72a34fu, 0x02d522d0u, 0x1585d978u, 0x02db40c0u, 0x00a6e141u, 0x0e5c2634u, 0x0030644eu};
-// same with p's limbs read from the constant bank (compiles to uniform-register operands)
-__global__ void k_uwide_cbank(uint64_t* out, uint32_t a0, int iters) {
-    uint32_t m[8];
-    for (int r = 0; r < 8; r++) m[r] = (uint32_t)out[r + (threadIdx.x & 1)] | 0x1000000u;
-    uint64_t t[8];
-    for (int i = 0; i < 8; i++) t[i] = i;
-    for (int k = 0; k < iters; k++) {
-#pragma unroll
-        for (int r = 0; r < 8; r++)
-#pragma unroll
-            for (int j = 0; j < 8; j++) t[j] += (uint64_t)m[r] * CP[j];
-    }
-    uint64_t x = 0;
-    for (int i = 0; i < 8; i++) x ^= t[i];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
-}
-// same with p's limbs in per-thread vector registers
-__global__ void k_uwide_regs(uint64_t* out, uint32_t a0, int iters) {
-    uint32_t m[8], p[8];
-    for (int r = 0; r < 8; r++) { m[r] = (uint32_t)out[r + (threadIdx.x & 1)] | 0x1000000u; p[r] = (uint32_t)out[r + 9 + (threadIdx.x & 1)] | 0x10000000u; }
-    uint64_t t[8];
-    for (int i = 0; i < 8; i++) t[i] = i;
-    for (int k = 0; k < iters; k++) {
-#pragma unroll
-        for (int r = 0; r < 8; r++)
-#pragma unroll
-            for (int j = 0; j < 8; j++) t[j] += (uint64_t)m[r] * p[j];
-    }
-    uint64_t x = 0;
-    for (int i = 0; i < 8; i++) x ^= t[i];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
-}
 
 
 // every multiply takes the low word of its own accumulator as multiplicand, so nothing is loop invariant (reg)
@@ -441,20 +314,10 @@ int main() {
     double nthr = (double)blocks * threads;
     double t;
     printf("{\"device\": \"%s\", \"sms\": %d", prop.name, sms);
-    t = time_ms([&] { k_wide<<<blocks, threads>>>((uint64_t*)buf, 0x9e3779b9u, 0x7f4a7c15u, iters); });          printf(", \"imad_wide_per_s\": %.4e", nthr * iters * 64 / (t * 1e-3));
-    t = time_ms([&] { k_wide_distinct<<<blocks, threads>>>((uint64_t*)buf, 0x9e3779b9u, 0x7f4a7c15u, iters); }); printf(", \"imad_wide_distinct_per_s\": %.4e", nthr * iters * 64 / (t * 1e-3));
     t = time_ms([&] { k_chain<<<blocks, threads>>>((uint32_t*)buf, 0x9e3779b9u, 0x7f4a7c15u, iters); });         printf(", \"imad_wide_carry_chain_mac_per_s\": %.4e", nthr * iters * 64 / (t * 1e-3));
     t = time_ms([&] { k_imad<<<blocks, threads>>>((uint32_t*)buf, 0x9e3779b9u, 0x7f4a7c15u, iters); });          printf(", \"imad_lo_per_s\": %.4e", nthr * iters * 64 / (t * 1e-3));
     t = time_ms([&] { k_addc<<<blocks, threads>>>((uint32_t*)buf, 0x9e3779b9u, iters); });                       printf(", \"iadd3_x_per_s\": %.4e", nthr * iters * 128 / (t * 1e-3));
     t = time_ms([&] { k_dfma<<<blocks, threads>>>((double*)buf, 1.000001, 0.999999, iters); });                  printf(", \"dfma_per_s\": %.4e", nthr * iters * 64 / (t * 1e-3));
-    t = time_ms([&] { k_dfma_wide<<<blocks, threads>>>((double*)buf, 1.000001, 0.999999, 3, 5, iters); });       printf(", \"dfma_plus_wide_pairs_per_s\": %.4e", nthr * iters * 32 / (t * 1e-3));
-    t = time_ms([&] { k_wide_alu<<<blocks, threads>>>((uint64_t*)buf, 0x9e3779b9u, 0x7f4a7c15u, iters); });      printf(", \"wide_plus_alu_pairs_per_s\": %.4e", nthr * iters * 32 / (t * 1e-3));
-    int it2 = 256;
-    t = time_ms([&] { k_swide_9x9<<<blocks, threads>>>((int64_t*)buf, 0x1234567, 0x7654321, it2); });   printf(", \"imad_wide_s32_9x9_per_s\": %.4e", nthr * it2 * 81 / (t * 1e-3));
-    t = time_ms([&] { k_uwide_9x9<<<blocks, threads>>>((uint64_t*)buf, 0x1234567, 0x7654321, it2); });  printf(", \"imad_wide_u32_9x9_per_s\": %.4e", nthr * it2 * 81 / (t * 1e-3));
-    t = time_ms([&] { k_uwide_imm<<<blocks, threads>>>((uint64_t*)buf, 0x1234567, it2); });             printf(", \"imad_wide_u32_imm_per_s\": %.4e", nthr * it2 * 64 / (t * 1e-3));
-    t = time_ms([&] { k_uwide_cbank<<<blocks, threads>>>((uint64_t*)buf, 0x1234567, it2); });           printf(", \"imad_wide_u32_cbank_per_s\": %.4e", nthr * it2 * 64 / (t * 1e-3));
-    t = time_ms([&] { k_uwide_regs<<<blocks, threads>>>((uint64_t*)buf, 0x1234567, it2); });            printf(", \"imad_wide_u32_regs_per_s\": %.4e", nthr * it2 * 64 / (t * 1e-3));
     int blocks2 = sms * 4;   // 64+ registers per thread: 4 x 256 threads per SM
     double nthr2 = (double)blocks2 * threads; int it3 = 4096;
     t = time_ms([&] { k_asm_u32_rr<<<blocks2, threads>>>((uint64_t*)buf, 0x1234567, 0x7654321, it3); }); printf(", \"asm_mad_wide_u32_distinct_regs_per_s\": %.4e", nthr2 * it3 * 32 / (t * 1e-3));
