@@ -188,6 +188,12 @@ long long zkv_wave_proofs(int device, int kernel);
 /* integer-pipe microbenchmark (roofline denominator): returns measured IMAD.WIDE.U32 results/s and
  * Fp-multiplications/s on `device` */
 int zkv_imad_peak(int device, double* wide_per_s, double* fpmul_per_s);
+/* Known-answer self test of the production kernels on `device`: the reference's two golden proofs (the RISC Zero seal and the SP1 proof
+ * of examples/{risc0,sp1}-verifier/examples/interact.rs, with the embedded keys of risc0/crypto.rs:16-79 and sp1/crypto.rs:7-81) must be
+ * accepted and a one-bit tamper of each rejected with VerificationFailed, in both kernel layouts.  0 = pass, ZKV_ERR_STATE = a kernel
+ * returned a wrong status (a miscompiled build: DESIGN.md section 5), other negatives as usual.  The Python mirror runs it once per
+ * process on the first device before the first call (ZKV_SKIP_SELFTEST=1 skips it). */
+int zkv_self_test(int device);
 
 #ifdef __cplusplus
 }

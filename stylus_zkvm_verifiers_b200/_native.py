@@ -59,6 +59,7 @@ _SIGS = {
     "zkv_launch_count": (C.c_ulonglong, []),
     "zkv_wave_proofs": (C.c_longlong, [C.c_int, C.c_int]),
     "zkv_imad_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "zkv_self_test": (C.c_int, [C.c_int]),
 }
 EXPORTS = tuple(_SIGS)
 
@@ -81,6 +82,14 @@ def lib():
         for name, (res, args) in _SIGS.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
+        # known-answer self test of the production kernels, once per process (zkv.h: zkv_self_test): a build whose kernels mis-verify the
+        # reference's golden proofs must not be used.  Runs on this process's own device (torchrun: LOCAL_RANK).
+        nd = L.zkv_device_count()
+        if nd > 0 and not os.environ.get("ZKV_SKIP_SELFTEST"):
+            dev = int(os.environ.get("LOCAL_RANK", "0"))
+            rc = L.zkv_self_test(dev if 0 <= dev < nd else 0)
+            if rc != 0:
+                raise ZkvError(rc, (L.zkv_last_error() or b"").decode())
         _lib = L
     return _lib
 

@@ -698,6 +698,34 @@ extern "C" int zkv_sp1_verify_batch_device(const zkv_sp1* h, int device, const v
     return rc;
 }
 
+
+// ------------------------------------------------------------------------------------------ known-answer self test (include/zkv.h)
+extern "C" int zkv_self_test(int device) {
+    if (zkv_device_count() <= device || device < 0) return fail(ZKV_ERR_CUDA, "no such CUDA device (this library has no CPU path)");
+    zkv_risc0* r0 = nullptr; zkv_sp1* s1 = nullptr;
+    int rc = zkv_risc0_create(nullptr, &device, 1, &r0);
+    if (!rc) rc = zkv_risc0_initialize(r0, ZKV_RISC0_FIXTURE_CONTROL_ROOT, ZKV_RISC0_FIXTURE_BN254_CONTROL_ID);
+    if (!rc) rc = zkv_sp1_create(nullptr, &device, 1, &s1);
+    for (int layout = 1; !rc && layout >= 0; layout--) {
+        uint8_t st[4] = {255, 255, 255, 255};
+        uint8_t seal[sizeof ZKV_RISC0_FIXTURE_SEAL], proof[sizeof ZKV_SP1_FIXTURE_PROOF];
+        memcpy(seal, ZKV_RISC0_FIXTURE_SEAL, sizeof seal); memcpy(proof, ZKV_SP1_FIXTURE_PROOF, sizeof proof);
+        zkv_vk_tune(zkv_risc0_vk(r0), ZKV_TUNE_LAYOUT, layout); zkv_vk_tune(zkv_sp1_vk(s1), ZKV_TUNE_LAYOUT, layout);
+        rc = zkv_risc0_verify(r0, seal, sizeof seal, ZKV_RISC0_FIXTURE_IMAGE_ID, ZKV_RISC0_FIXTURE_JOURNAL_DIGEST, &st[0]);
+        seal[4 + 100] ^= 0x04;                               // one bit of B: still a field element, no longer a valid proof
+        if (!rc) rc = zkv_risc0_verify(r0, seal, sizeof seal, ZKV_RISC0_FIXTURE_IMAGE_ID, ZKV_RISC0_FIXTURE_JOURNAL_DIGEST, &st[1]);
+        if (!rc) rc = zkv_sp1_verify_proof(s1, ZKV_SP1_FIXTURE_VKEY, ZKV_SP1_FIXTURE_PUBLIC_VALUES, sizeof ZKV_SP1_FIXTURE_PUBLIC_VALUES, proof, sizeof proof, &st[2]);
+        uint8_t vkey[32]; memcpy(vkey, ZKV_SP1_FIXTURE_VKEY, 32); vkey[31] ^= 1;      // another program key: a different public input
+        if (!rc) rc = zkv_sp1_verify_proof(s1, vkey, ZKV_SP1_FIXTURE_PUBLIC_VALUES, sizeof ZKV_SP1_FIXTURE_PUBLIC_VALUES, proof, sizeof proof, &st[3]);
+        if (!rc && !(st[0] == ZKV_OK && st[2] == ZKV_OK && st[1] != ZKV_OK && st[1] != 255 && st[3] == ZKV_VERIFICATION_FAILED)) {
+            char msg[160]; snprintf(msg, sizeof msg, "zkv_self_test: kernels (layout %d) returned statuses %d %d %d %d for the reference's golden proofs and their tampers; expected 0, reject, 0, 1", layout, st[0], st[1], st[2], st[3]);
+            rc = fail(ZKV_ERR_STATE, msg);
+        }
+    }
+    if (r0) zkv_risc0_destroy(r0);
+    if (s1) zkv_sp1_destroy(s1);
+    return rc;
+}
 // ------------------------------------------------------------------------------------------ pairing service (0x08 seam)
 static int pairing4_chain(DevCtx* c, const zkv_vk* vk, size_t o, int n, const uint8_t* d_g1s, const uint8_t* d_g2s, uint8_t* d_ok, uint8_t* d_gt, uint8_t* d_miller, cudaStream_t s, bool timed) {
     uint8_t* flags = c->flags + o;

@@ -354,6 +354,11 @@ def g2_check_batch(g2s, n, device=0):
     return out
 
 
+def device_count():
+    """number of CUDA devices the library sees (0 without a driver)"""
+    return int(N.lib().zkv_device_count())
+
+
 def wave_proofs(device, kernel):
     """Proofs in one full wave of the verification Miller-loop kernel (kernel 0) or the final exponentiation (kernel 1) on `device`;
     2 / 3 = the same for the round-1 layout."""

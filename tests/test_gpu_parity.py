@@ -571,3 +571,46 @@ def test_general_ec_pairing_service_vs_oracle(Z, gpu):
     one = O.w32(1)
     assert Z.ec_pairing(b"") == one and Z.ec_pairing(G1 + bytes(128)) == one and Z.ec_pairing(G1 + G2) == O.w32(0)
     assert Z.ec_pairing((G1 + G2)[:-1]) is None and Z.ec_pairing(G1 + G2 + neg(G1) + G2) == one
+
+
+def test_one_handle_across_all_devices_matches_one_device(Z, gpu, fx):
+    """North star: 'partitioned across the GPUs ... results gathered on the host'.  ONE handle created over devices [0..N-1] splits a mixed
+    batch call into contiguous ranges (for_each_device in csrc/zkv.cu), one host thread per device, and gathers the status bytes; they must
+    equal the single-device handle's bytes everywhere and the oracle's on a prefix and on the range boundaries.  Skipped on a 1-GPU box."""
+    import torch
+    nd = Z.device_count() if hasattr(Z, "device_count") else torch.cuda.device_count()
+    if nd < 2:
+        pytest.skip("needs at least two CUDA devices")
+    from stylus_zkvm_verifiers_b200 import synth as S
+    devs = list(range(nd))
+    n = 1 << 17
+    for shape in ("risc0", "sp1"):
+        if shape == "risc0":
+            vk = S.make_vk(gpu, 0, 6, 0xB2000001)
+            mk = lambda d: Z.RiscZeroVerifier(Z.VerificationKey(0, vk.alpha, vk.beta, vk.gamma, vk.delta, vk.ic, devices=d), devices=d)
+            one, many = mk([0]), mk(devs)
+            for v in (one, many):
+                v.initialize(fx["control_root"], fx["bn254_control_id"])
+            b = S.make_risc0_batch(gpu, vk, one.get_selector(), fx["control_root"], fx["bn254_control_id"], fx["sys0"], n, 0xB2000021, pool=512)
+            S.mutate_risc0(b, gpu, S.SplitMix64(0xB2000022))
+            run = lambda v: v.verify_batch(b.seals, b.image_ids, b.journals)
+            ro = O.Risc0Oracle(oracle_vk(vk)); ro.initialize(fx["control_root"], fx["bn254_control_id"])
+            oracle = lambda idx: ro.verify_batch([b.seals[i] for i in idx], [b.image_ids[i] for i in idx], [b.journals[i] for i in idx])
+        else:
+            vk = S.make_vk(gpu, 1, 3, 0xB2000003)
+            mk = lambda d: Z.Sp1Verifier(Z.VerificationKey(1, vk.alpha, vk.beta, vk.gamma, vk.delta, vk.ic, devices=d), devices=d)
+            one, many = mk([0]), mk(devs)
+            b = S.make_sp1_batch(gpu, vk, n, 0xB2000023, pool=512)
+            S.mutate_sp1(b, gpu, S.SplitMix64(0xB2000024))
+            run = lambda v: v.verify_batch(b.vkeys, b.public_values, b.proofs)
+            ovk = oracle_vk(vk)
+            oracle = lambda idx: O.sp1_verify_batch(ovk, S.SP1_SELECTOR, [b.vkeys[i] for i in idx], [b.public_values[i] for i in idx], [b.proofs[i] for i in idx])
+        a, m = np.asarray(run(one)), np.asarray(run(many))
+        assert a.shape == m.shape == (n,) and (a == m).all(), (shape, int((a != m).sum()))
+        idx = list(range(512))
+        for d in range(1, nd):                      # both sides of every device-range boundary
+            cut = n * d // nd
+            idx += list(range(cut - 32, cut + 32))
+        want = np.asarray(oracle(idx))
+        assert (m[idx] == want).all(), shape
+        assert 0 < int((m == 0).sum()) < n and len(set(m.tolist())) >= 3
