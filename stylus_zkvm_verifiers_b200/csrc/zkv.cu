@@ -55,7 +55,7 @@ static const uint8_t FR_R_BE[32] = {0x30, 0x64, 0x4e, 0x72, 0xe1, 0x31, 0xa0, 0x
 
 // ------------------------------------------------------------------------------------------ per-device context
 struct DevCtx {
-    int device = 0;
+    int device = 0, sms = 148;
     cudaStream_t stream = nullptr;
     // per-vk tables (device memory, Montgomery form)
     VkDev* d_vk = nullptr; line_t* d_lines = nullptr; nline_t* d_nlines = nullptr; fp12* d_pre = nullptr; g1aff* d_tab = nullptr; g1aff* d_ic0 = nullptr;
@@ -84,7 +84,7 @@ struct DevCtx {
 
 // Tuning of one key handle (zkv_vk_tune): no process-wide mutable state.  Read once per batch call.
 struct Tuning {
-    std::atomic<int> overlap_chunks{4};     // a device batch is cut into this many kernel chains on side streams
+    std::atomic<int> overlap_chunks{0};     // a device batch is cut into this many kernel chains on side streams; 0 = automatic (chunk_count)
     std::atomic<int> normalised_lines{1};   // verification path: gamma / delta lines scaled to (1, n3, n4)
     std::atomic<int> miller_segments{8};    // chunked batches: segment kernels per Miller loop (state in HBM between them)
     std::atomic<int> final_exp_stages{1};   // chunked batches: the final exponentiation as four stage kernels
@@ -154,6 +154,7 @@ static DevCtx* vk_ctx(const zkv_vk* vk, int device) { for (auto* c : vk->devs) i
 
 static int vk_build_on(zkv_vk* vk, DevCtx* c) {
     CK(cudaSetDevice(c->device));
+    CK(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, c->device));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
     for (auto& a : c->aux) CK(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
@@ -249,7 +250,7 @@ extern "C" int zkv_vk_tune(const void* handle_vk, int option, int value) {
     if (!vk) return fail(ZKV_ERR_ARG, "zkv_vk_tune: null key");
     std::atomic<int>* f; int lo, hi;
     switch (option) {
-        case ZKV_TUNE_OVERLAP: f = &vk->tune.overlap_chunks; lo = 1; hi = 64; break;
+        case ZKV_TUNE_OVERLAP: f = &vk->tune.overlap_chunks; lo = 0; hi = 64; break;
         case ZKV_TUNE_NORMALISED_LINES: f = &vk->tune.normalised_lines; lo = 0; hi = 1; break;
         case ZKV_TUNE_MILLER_SEGMENTS: f = &vk->tune.miller_segments; lo = 1; hi = 16; break;
         case ZKV_TUNE_FINAL_EXP_STAGES: f = &vk->tune.final_exp_stages; lo = 0; hi = 1; break;
@@ -338,6 +339,16 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
     CK(cudaGetLastError());
     return 0;
 }
+// Chunks of a device batch.  Automatic (setting 0): half a wave of the heavy kernels each (2 resident blocks of 128 threads per SM, so half a
+// wave = SMs x 128 proofs), evened out: two chunks are co-resident at any time, the block scheduler back-fills one chunk's partial wave with
+// the other's blocks, and what a batch can lose at its end is half a wave whatever its size (2^16 proofs on 148 SMs: 4 chunks of 16 384;
+// 2^17: 7 chunks of 18 816 instead of 4 x 32 768, each of which would occupy a whole wave's slots for 86 % of a wave's work).
+static int chunk_count(const DevCtx* c, size_t n, int setting) {
+    if (n < (size_t)8192) return 1;
+    if (setting >= 1) return setting;
+    const size_t half = (size_t)c->sms * ZKV_HTPB;
+    return (int)std::min<size_t>(64, std::max<size_t>(1, (n + half - 1) / half));
+}
 // Fork `chunks` side streams off `main`, run fn(chunk_begin, chunk_len, stream) on them round-robin, join back into `main`.
 // Chunk boundaries are multiples of the heavy kernels' block size so no chunk carries a second partial block.
 template <class F>
@@ -361,8 +372,8 @@ static int run_verify(DevCtx* c, const Job& j) {
     int rc = ctx_acquire(c, c->stream); if (rc) return rc;
     if (c->busy && (j.n > c->cap || j.n > c->fes_cap || j.n * (size_t)ns * 8 > c->scal_words)) { CK(cudaEventSynchronize(c->ev_busy)); c->busy = false; }   // growing frees buffers an earlier asynchronous call may still use
     rc = ctx_reserve(c, j.n, (size_t)ns * 8); if (rc) return rc;
-    int chunks = j.vk->tune.overlap_chunks.load();
-    if (j.n < (size_t)8192 || chunks <= 1) return enqueue_chain(c, j, 0, 0, (int)j.n, c->stream, true);
+    int chunks = chunk_count(c, j.n, j.vk->tune.overlap_chunks.load());
+    if (chunks <= 1) return enqueue_chain(c, j, 0, 0, (int)j.n, c->stream, true);
     return fork_join(c, c->stream, j.n, chunks, [&](size_t o, int m, cudaStream_t s) { return enqueue_chain(c, j, o, o, m, s, false); });
 }
 static void collect_stage_ms(DevCtx* c);
@@ -376,8 +387,7 @@ template <class Pack, class MakeJob>
 static int host_pipeline(DevCtx* c, const zkv_vk* vk, size_t m, size_t in_bytes, int ns, Pack pack, MakeJob job) {
     if (c->busy) { CK(cudaEventSynchronize(c->ev_busy)); c->busy = false; }      // a host call blocks anyway: wait out an earlier asynchronous device call here
     int rc = ctx_reserve(c, m, (size_t)ns * 8); if (rc) return rc;
-    const int oc = vk->tune.overlap_chunks.load();
-    int chunks = (m < (size_t)8192 || oc <= 1) ? 1 : oc;
+    int chunks = chunk_count(c, m, vk->tune.overlap_chunks.load());
     size_t per = (m + chunks - 1) / chunks;
     per = (per + ZKV_HTPB - 1) / ZKV_HTPB * ZKV_HTPB;
     chunks = (int)((m + per - 1) / per);
@@ -388,20 +398,28 @@ static int host_pipeline(DevCtx* c, const zkv_vk* vk, size_t m, size_t in_bytes,
     for (int k = 0; k < chunks; k++) { size_t first = per * (size_t)k; bytes[k] = pack(first, std::min(per, m - first), nullptr); offs[k + 1] = offs[k] + (bytes[k] + 255) / 256 * 256; }
     (void)in_bytes;
     rc = ctx_stage(c, offs[chunks], m); if (rc) return rc;
+    // chunk 0 is packed here, the others by up to 6 helper threads (helper h packs chunks h + 1, h + 1 + H, ...); ready[k] flips when chunk k's
+    // block is complete, and the enqueue loop below waits for it right before the chunk's upload
+    const int H = std::min(chunks - 1, 6);
+    std::vector<std::atomic<int>> ready(chunks);
+    for (auto& r : ready) r.store(0);
     std::vector<std::thread> helpers;
-    for (int k = 1; k < chunks; k++) helpers.emplace_back([&, k]() { size_t first = per * (size_t)k; pack(first, std::min(per, m - first), c->h_pin + offs[k]); });
-    pack(0, std::min(per, m), c->h_pin);
+    for (int h = 0; h < H; h++) helpers.emplace_back([&, h]() {
+        for (int k = h + 1; k < chunks; k += H) { size_t first = per * (size_t)k; pack(first, std::min(per, m - first), c->h_pin + offs[k]); ready[k].store(1, std::memory_order_release); }
+    });
+    pack(0, std::min(per, m), c->h_pin); ready[0].store(1);
     int used = 0;
-    for (int k = 0; k < chunks; k++) {
+    for (int k = 0; k < chunks && !rc; k++) {
         const size_t first = per * (size_t)k, cnt = std::min(per, m - first), in_off = offs[k];
         cudaStream_t s = chunks == 1 ? c->stream : c->aux[k % DevCtx::NAUX];
         if (chunks > 1) used = std::max(used, k % DevCtx::NAUX + 1);
-        if (k) helpers[k - 1].join();
+        while (!ready[k].load(std::memory_order_acquire)) std::this_thread::yield();
         rc = cudaMemcpyAsync(c->d_in + in_off, c->h_pin + in_off, bytes[k], cudaMemcpyHostToDevice, s) == cudaSuccess ? 0 : fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (host to device)");
         if (!rc) { Job j = job(first, cnt, c->d_in + in_off); rc = enqueue_chain(c, j, 0, first, (int)cnt, s, chunks == 1); }
         if (!rc && cudaMemcpyAsync(c->h_out + first, c->d_out + first, cnt, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (device to host)");
-        if (rc) { for (int t = k; t < chunks - 1; t++) helpers[t].join(); return rc; }
     }
+    for (auto& t : helpers) t.join();
+    if (rc) { cudaDeviceSynchronize(); return rc; }
     if (chunks == 1) { CK(cudaStreamSynchronize(c->stream)); collect_stage_ms(c); }
     else for (int a = 0; a < used; a++) CK(cudaStreamSynchronize(c->aux[a]));
     return 0;
@@ -768,8 +786,8 @@ static int run_pairing4(DevCtx* c, const zkv_vk* vk, size_t n_, const uint8_t* d
         for (int e = 0; e < 6; e++) CK(cudaEventRecord(c->ev[e], s));
         return 0;
     }
-    int chunks = vk->tune.overlap_chunks.load();
-    if (n_ < (size_t)8192 || chunks <= 1) return pairing4_chain(c, vk, 0, (int)n_, d_g1s, d_g2s, d_ok, d_gt, d_miller, s, true);
+    int chunks = chunk_count(c, n_, vk->tune.overlap_chunks.load());
+    if (chunks <= 1) return pairing4_chain(c, vk, 0, (int)n_, d_g1s, d_g2s, d_ok, d_gt, d_miller, s, true);
     return fork_join(c, s, n_, chunks, [&](size_t o, int m, cudaStream_t st) { return pairing4_chain(c, vk, o, m, d_g1s, d_g2s, d_ok, d_gt, d_miller, st, false); });
 }
 extern "C" int zkv_pairing4_batch(const zkv_vk* vk, const uint8_t* g1s, const uint8_t* g2s, size_t n, uint8_t* ok_out, uint8_t* gt_out, uint8_t* miller_out) {

@@ -475,11 +475,22 @@ def test_launch_counter_and_wave_size(Z, gpu, fx):
     assert Z.launch_count() - c0 == 6                      # one serial chain: decode, signals, vk_x, G2 check, Miller loop, final exponentiation
     n = 8192 + 300
     big = S.make_risc0_batch(gpu, vk, v.get_selector(), fx["control_root"], fx["bn254_control_id"], fx["sys0"], n, 0xB200000E, pool=8)
+    assert v.tune("overlap") == 0                          # default: automatic, half-wave chunks (SMs x 128 proofs) -> this batch is one chain
+    c0 = Z.launch_count()
+    assert set(v.verify_batch(big.seals, big.image_ids, big.journals).tolist()) == {0}
+    assert Z.launch_count() - c0 == 6
+    v.tune("overlap", 4)
     chunks, segs, fe = v.tune("overlap"), v.tune("miller_segments"), v.tune("final_exp_stages")
     c0 = Z.launch_count()
     assert set(v.verify_batch(big.seals, big.image_ids, big.journals).tolist()) == {0}
     per_chain = 4 + segs + (4 if fe else 1)
-    assert Z.launch_count() - c0 == chunks * per_chain
+    assert chunks == 4 and Z.launch_count() - c0 == chunks * per_chain
+    v.tune("overlap", 0)
+    m = sms * 128 * 2 + 1                                  # just over two half-waves -> three chunks
+    mid = S.make_risc0_batch(gpu, vk, v.get_selector(), fx["control_root"], fx["bn254_control_id"], fx["sys0"], m, 0xB200000F, pool=8)
+    c0 = Z.launch_count()
+    assert set(v.verify_batch(mid.seals, mid.image_ids, mid.journals).tolist()) == {0}
+    assert Z.launch_count() - c0 == 3 * per_chain
 
 
 def test_concurrent_calls_on_shared_and_separate_handles(Z, gpu, fx):
