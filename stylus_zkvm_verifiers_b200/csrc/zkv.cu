@@ -73,8 +73,8 @@ struct DevCtx {
     // overlap: a batch is cut into chunks whose kernel chains run on side streams, so the block scheduler back-fills the partial last
     // wave of one chunk's kernel with blocks of another chunk's (see run_verify)
     static constexpr int NAUX = 4;
-    cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t aux[NAUX] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {};
     // The workspace above is shared by every call on this key and device.  Host-buffer calls return only when their work is done; the
     // *_device calls are asynchronous, so each records `ev_busy` behind its last kernel and every later user of the workspace, on whatever
     // stream, first waits for it (ctx_acquire).

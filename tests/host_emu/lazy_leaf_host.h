@@ -47,6 +47,18 @@ static inline void lz_addhi(uint32_t* r, const uint32_t* x, const uint32_t* c) {
     if (cy) lz_die("addhi carry");
     for (int i = 0; i < 16; i++) r[i] = t[i];
 }
+static inline void lz_hi_chain(uint32_t* r, const uint32_t* x, const uint32_t* n, int sub, const char* what) {
+    uint32_t t[16]; uint64_t c = 0;
+    for (int i = 0; i < 8; i++) t[i] = x[i];
+    for (int i = 0; i < 8; i++) {
+        if (sub) { uint64_t d = (uint64_t)x[8 + i] - n[i] - c; t[8 + i] = (uint32_t)d; c = (d >> 63) & 1; }
+        else { c += (uint64_t)x[8 + i] + n[i]; t[8 + i] = (uint32_t)c; c >>= 32; }
+    }
+    if (c) lz_die(what);
+    for (int i = 0; i < 16; i++) r[i] = t[i];
+}
+static inline void lz_addw_hi(uint32_t* r, const uint32_t* x, const uint32_t* n) { lz_hi_chain(r, x, n, 0, "addw_hi carry"); }
+static inline void lz_subw_hi(uint32_t* r, const uint32_t* x, const uint32_t* n) { lz_hi_chain(r, x, n, 1, "subw_hi borrow"); }
 static inline void lz_csub_top(uint32_t* r, const uint32_t* x, const uint32_t* k, int n) {
     uint32_t t[8]; uint64_t bo = 0; int lo = n - 8;
     for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)x[lo + i] - k[i] - bo; t[i] = (uint32_t)d; bo = (d >> 63) & 1; }

@@ -127,6 +127,16 @@ def test_lazy_generator_bounds_and_current_header():
     assert open(os.path.join(ROOT, "stylus_zkvm_verifiers_b200", "csrc", "lazy_gen.cuh")).read() == g.render()
 
 
+def test_two_lane_generator_bounds_and_current_header():
+    """tools/gen_lazy2.py (two lanes per proof, the measured alternative layout of DESIGN.md section 5) proves the bounds of its routines for
+    both lanes and checks their values against plain modular arithmetic; csrc/lazy2_gen.cuh is what it emits."""
+    import importlib.util
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    spec = importlib.util.spec_from_file_location("gen_lazy2", os.path.join(ROOT, "tools", "gen_lazy2.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    assert open(os.path.join(ROOT, "stylus_zkvm_verifiers_b200", "csrc", "lazy2_gen.cuh")).read() == g.render()
+
+
 def test_lazy_tower_on_slots_matches_round1_tower(emu):
     """csrc/lazy.cuh (shared-memory slots, lazily reduced Fp6 routines) against the round-1 tower and the oracle, including all-(p-1),
     all-zero and mixed-extreme operands; the portable leaves abort on any carry, borrow or reduction-range violation."""

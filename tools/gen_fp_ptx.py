@@ -57,6 +57,9 @@ class Prog:
             if op == "assert_nc":
                 assert cf == 0, "dropped carry in %s" % self.name
                 continue
+            if op == "assert_zero":
+                assert src[0] == 0, "overflow beyond the top limb in %s" % self.name
+                continue
             if op in ("mul.lo", "mul.hi"):
                 pr = src[0] * src[1]
                 reg[dst] = (pr & MASK) if op == "mul.lo" else (pr >> 32)
@@ -113,7 +116,7 @@ class Prog:
         lines.append(".reg .pred q;")
         for ins in self.code:
             op, dst, src = ins[0], ins[1], ins[2:]
-            if op == "assert_nc":
+            if op in ("assert_nc", "assert_zero"):
                 continue
             if op == "selp_eqz":
                 lines.append("setp.eq.u32 q, %s, 0;" % fmt(src[2]))
@@ -245,6 +248,52 @@ def mul_wide(p, a, b):
         out.append(p.op("addc.cc", E[k + 1], O[k]))
     out.append(p.op("addc.cc", O[7], 0))
     p.emit("assert_nc", None)
+    return out
+
+
+def mul_wide2(p, a, b, c, d):
+    """16-limb a b + c d for 8-limb operands whose product sum stays below 2^512 (asserted): 128 IMAD.WIDE and no wide addition.
+    Same even / odd framing as mul_wide; at every offset the row of a and the row of c land on the same accumulators, and the carry
+    out of limb offset + 8 is kept in TOP, which enters the odd accumulator of limb offset + 9 at the next slide."""
+    out = []
+    E, O = [None] * N, [None] * N
+    for j in (0, 2, 4, 6):
+        E[j] = p.op("mul.lo", a[j], b[0]); E[j + 1] = p.op("mul.hi", a[j], b[0])
+    for j in (1, 3, 5, 7):
+        O[j - 1] = p.op("mul.lo", a[j], b[0]); O[j] = p.op("mul.hi", a[j], b[0])
+    top = 0
+    for i in range(N):
+        if i:
+            X = E[1]
+            Oin = E[2:] + [0, top]
+            E = O
+            O = [None] * N
+            E[0] = p.op("add.cc", E[0], X)
+            for j in (1, 3, 5, 7):
+                O[j - 1] = p.op("madc.lo.cc", a[j], b[i], Oin[j - 1])
+                O[j] = p.op("madc.hi.cc", a[j], b[i], Oin[j])
+            top = p.op("addc", 0, 0)
+            for idx, j in enumerate((0, 2, 4, 6)):
+                E[j] = p.op("mad.lo.cc" if idx == 0 else "madc.lo.cc", a[j], b[i], E[j])
+                E[j + 1] = p.op("madc.hi.cc", a[j], b[i], E[j + 1])
+            O[7] = p.op("addc.cc", O[7], 0)
+            top = p.op("addc", top, 0)
+        for idx, j in enumerate((1, 3, 5, 7)):
+            O[j - 1] = p.op("mad.lo.cc" if idx == 0 else "madc.lo.cc", c[j], d[i], O[j - 1])
+            O[j] = p.op("madc.hi.cc", c[j], d[i], O[j])
+        top = p.op("addc", top, 0)
+        for idx, j in enumerate((0, 2, 4, 6)):
+            E[j] = p.op("mad.lo.cc" if idx == 0 else "madc.lo.cc", c[j], d[i], E[j])
+            E[j + 1] = p.op("madc.hi.cc", c[j], d[i], E[j + 1])
+        O[7] = p.op("addc.cc", O[7], 0)
+        top = p.op("addc", top, 0)
+        out.append(E[0])
+    out.append(p.op("add.cc", E[1], O[0]))
+    for k in range(1, 7):
+        out.append(p.op("addc.cc", E[k + 1], O[k]))
+    out.append(p.op("addc.cc", O[7], 0))
+    p.emit("assert_nc", None)
+    p.emit("assert_zero", None, top)
     return out
 
 
@@ -382,6 +431,14 @@ def gen_mulw():
     return p
 
 
+def gen_mulw2():
+    p = Prog("lz_mulw2", nm("a") + nm("b") + nm("c") + nm("d"), nm("w", 16))
+    out = mul_wide2(p, nm("a"), nm("b"), nm("c"), nm("d"))
+    for k in range(16):
+        p.emit("mov", "w%d" % k, out[k])
+    return p
+
+
 def gen_redc_nf():
     """r = (T + m p) / 2^256 for a 16-limb T < 4 p 2^256, WITHOUT the final subtraction: r < T / 2^256 + p < 5 p < 2^256."""
     p = Prog("lz_redc", nm("w", 16), nm("r"))
@@ -426,6 +483,17 @@ def gen_addhi():
     return p
 
 
+def gen_hi(name, op):
+    """r = x op (n * 2^256) for a 16-limb x and an 8-limb n (op in add, sub): only the upper half moves; no carry / borrow out."""
+    p = Prog(name, nm("x", 16) + nm("n", 8), nm("r", 16))
+    for k in range(8):
+        p.emit("mov", "r%d" % k, "x%d" % k)
+    for k in range(8):
+        p.emit(("%s.cc" % op) if k == 0 else ("%sc.cc" % op), "r%d" % (8 + k), "x%d" % (8 + k), "n%d" % k)
+    p.emit("assert_nc", None)
+    return p
+
+
 def gen_csub(name, n):
     """the top 8 limbs of an n-limb x (n = 8 or 16) minus the 8-limb constant k if that does not borrow, else unchanged."""
     p = Prog(name, nm("x", n) + nm("k", 8), nm("r", n))
@@ -441,7 +509,7 @@ def gen_csub(name, n):
 
 def leaf_progs():
     return [gen_mulw(), gen_redc_nf(), gen_chain("lz_add8", "add", 8), gen_chain("lz_sub8", "sub", 8), gen_chain("lz_addw", "add", 16),
-            gen_chain("lz_subw", "sub", 16), gen_addhi(), gen_csub("lz_csubw", 16), gen_csub("lz_csub8", 8)]
+            gen_chain("lz_subw", "sub", 16), gen_addhi(), gen_csub("lz_csubw", 16), gen_csub("lz_csub8", 8), gen_hi("lz_addw_hi", "add"), gen_hi("lz_subw_hi", "sub"), gen_mulw2()]
 
 
 def check_leaves(iters=600):
@@ -453,13 +521,20 @@ def check_leaves(iters=600):
         for c, (x, n) in kw.items():
             inp.update({"%s%d" % (c, i): v for i, v in lim(x, n).items()})
         return val(prog.run(inp))
-    mulw, redc, add8, sub8, addw, subw, addhi, csubw, csub8 = leaf_progs()
+    mulw, redc, add8, sub8, addw, subw, addhi, csubw, csub8, addw_hi, subw_hi, mulw2 = leaf_progs()
     Bw = P << 256
     for it in range(iters):
         a, b = rnd.getrandbits(256), rnd.getrandbits(256)
         if it < 4:
             a, b = [(0, 0), ((1 << 256) - 1, (1 << 256) - 1), (P - 1, P - 1), (1, (1 << 256) - 1)][it]
         assert run(mulw, a=(a, 8), b=(b, 8)) == a * b
+        c2, d2 = rnd.getrandbits(256), rnd.getrandbits(256)
+        a2, b2 = a, b
+        if it < 4:
+            c2, d2 = [((1 << 256) - 1, 1 << 255), (0, 0), ((1 << 256) - 1, (1 << 256) - 1), (P - 1, P - 1)][it]
+        while a2 * b2 + c2 * d2 >= 1 << 512:
+            a2 >>= 1; c2 >>= 1
+        assert run(mulw2, a=(a2, 8), b=(b2, 8), c=(c2, 8), d=(d2, 8)) == a2 * b2 + c2 * d2, "mulw2"
         t = rnd.randrange(4 * Bw) if it > 3 else [0, 4 * Bw - 1, Bw, Bw - 1][it]
         r = run(redc, w=(t, 16))
         assert r < (t >> 256) + P + 1 and (r << 256) % P == t % P, "redc"
@@ -467,6 +542,10 @@ def check_leaves(iters=600):
         assert run(add8, a=(x, 8), b=(y, 8)) == x + y and run(sub8, a=(y, 8), b=(x, 8)) == y - x
         x, y = sorted((rnd.getrandbits(511), rnd.getrandbits(511)))
         assert run(addw, a=(x, 16), b=(y, 16)) == x + y and run(subw, a=(y, 16), b=(x, 16)) == y - x
+        nn = rnd.getrandbits(255)
+        assert run(addw_hi, x=(x, 16), n=(nn, 8)) == x + (nn << 256)
+        big = x | (1 << 511)
+        assert run(subw_hi, x=(big, 16), n=(nn, 8)) == big - (nn << 256)
         c = rnd.randrange(1 << 32) * P
         assert run(addhi, x=(x, 16), c=(c, 9)) == x + (c << 224)
         k = rnd.randrange(1, 5)
@@ -483,6 +562,8 @@ LEAF_SIGS = {
     "lz_addw": "uint32_t* r, const uint32_t* a, const uint32_t* b", "lz_subw": "uint32_t* r, const uint32_t* a, const uint32_t* b",
     "lz_addhi": "uint32_t* r, const uint32_t* x, const uint32_t* c", "lz_csubw": "uint32_t* r, const uint32_t* x, const uint32_t* k",
     "lz_csub8": "uint32_t* r, const uint32_t* x, const uint32_t* k",
+    "lz_addw_hi": "uint32_t* r, const uint32_t* x, const uint32_t* n", "lz_subw_hi": "uint32_t* r, const uint32_t* x, const uint32_t* n",
+    "lz_mulw2": "uint32_t* w, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d",
 }
 
 

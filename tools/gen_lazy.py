@@ -42,7 +42,7 @@ class Atom:
         self.name, self.hi, self.vals = name, hi, vals      # value in [0, hi)
 
 
-class Nv:
+class Nv:  # (see R_ATOM below: the constant 2^256 as an atom, so that n * 2^256 has an exact linear form)
     """narrow value: 8 limbs, a non-negative integer combination of atoms"""
     def __init__(self, name, lin, vals, canon=False):
         self.name, self.lin, self.vals, self.canon = name, lin, vals, canon
@@ -65,6 +65,9 @@ class Wv:
 
     def hi(self):    # inclusive maximum of the stored value
         return self.off + sum(c * Wv.kmax(k) for k, c in self.lin.items() if c > 0)
+
+
+R_ATOM = Atom("R", R + 1, [R] * NCASE)
 
 
 def lin_add(a, b, sb=1):
@@ -178,7 +181,19 @@ class Gen:
         self.emit("lz_mulw(%s, %s, %s);" % (w.name, a.name, b.name))
         return w
 
+    def hiw(self, n):
+        """n * 2^256 as a VIRTUAL wide value (never materialised): addw / subw add or subtract it on the upper eight limbs only.
+        With n a Montgomery residue x R this is x R^2, the scale of the products, so redc(T -+ hiw(n)) = redc(T) -+ n (mod p)."""
+        lin = {}
+        for ka, ca in n.lin.items():
+            lin[(ka, R_ATOM) if id(ka) <= id(R_ATOM) else (R_ATOM, ka)] = ca
+        w = Wv("hi:" + n.name, lin, 0, [v << 256 for v in n.vals])
+        w.hi_src = n.name
+        assert w.hi() < LIM
+        return w
+
     def csub(self, x, k):
+        assert not getattr(x, "hi_src", None), "a virtual n * 2^256 value cannot be reduced"
         self.stats["csubw"] += 1
         assert 1 <= k <= 4 and x.lo() >= 0
         hi = max(k * BW - 1, x.hi() - k * BW)
@@ -202,7 +217,7 @@ class Gen:
         return x
 
     def addoff(self, x, off):
-        assert off % UNIT == 0 and off > 0
+        assert off % UNIT == 0 and off > 0 and not getattr(x, "hi_src", None)
         self.stats["addhi"] += 1
         x = self.ensure(x, LIM - 1 - off)
         w = self._w(x.lin, x.off + off, [v + off for v in x.vals])
@@ -211,13 +226,20 @@ class Gen:
 
     def addw(self, a, b):
         self.stats["wide_addsub"] += 1
+        if getattr(a, "hi_src", None):
+            a, b = b, a
+        assert not getattr(a, "hi_src", None)
+        vb = getattr(b, "hi_src", None)
         while a.hi() + b.hi() >= LIM:
-            if a.hi() >= b.hi():
+            if a.hi() >= b.hi() or vb:
                 a = self.ensure(a, max(BW - 1, a.hi() // 2))
             else:
                 b = self.ensure(b, max(BW - 1, b.hi() // 2))
         w = self._w(lin_add(a.lin, b.lin), a.off + b.off, [x + y for x, y in zip(a.vals, b.vals)])
-        self.emit("lz_addw(%s, %s, %s);" % (w.name, a.name, b.name))
+        if vb:
+            self.emit("lz_addw_hi(%s, %s, %s);" % (w.name, a.name, vb))
+        else:
+            self.emit("lz_addw(%s, %s, %s);" % (w.name, a.name, b.name))
         return w
 
     def subw(self, a, b):
@@ -231,7 +253,11 @@ class Gen:
             need = -probe.lo()
             a = self.addoff(a, -(-need // UNIT) * UNIT)      # (may first reduce a, which forgets its expression: hence the loop)
         w = self._w(lin, a.off - b.off, [x - y for x, y in zip(a.vals, b.vals)])
-        self.emit("lz_subw(%s, %s, %s);" % (w.name, a.name, b.name))
+        assert not getattr(a, "hi_src", None)
+        if getattr(b, "hi_src", None):
+            self.emit("lz_subw_hi(%s, %s, %s);" % (w.name, a.name, b.hi_src))
+        else:
+            self.emit("lz_subw(%s, %s, %s);" % (w.name, a.name, b.name))
         return w
 
     def dblw(self, a):
@@ -413,8 +439,115 @@ def gen_f4sqr():
     return g, [o0, o1]
 
 
+def st2(g, base, i, v):
+    g.st(base, 2 * i, v[0]); g.st(base, 2 * i + 1, v[1])
+
+
+def w2_addhi(g, w, n, sign=1):
+    """w +- n * 2^256 for an Fp2 pair of wide values w and an Fp2 pair of narrow values n"""
+    op = g.addw if sign > 0 else g.subw
+    return op(w[0], g.hiw(n[0])), op(w[1], g.hiw(n[1]))
+
+
+def gen_f6mul01_acc(kind):
+    g = Gen("lz_f6mul01_" + kind, 5 if kind == "add" else 6)
+    A = [ld2(g, "a", 0), ld2(g, "a", 1), None]
+    Bv = [ld2(g, "b", 0), ld2(g, "b", 1)]
+    Cv = [None] * 3
+    outs = [None] * 3
+    tgt = {"add": (1, 2, 0), "vadd": (2, 0, 1)}[kind]            # where (ab).c1, (ab).c2, (ab).c0 go: o = c + ab, or o = c + v ab
+    v0 = f2_mulw(g, A[0], Bv[0])
+    v1 = f2_mulw(g, A[1], Bv[1])
+    m01 = f2_mulw(g, f2_add8(g, A[0], A[1]), f2_add8(g, Bv[0], Bv[1]))
+    x = w2_sub(g, w2_sub(g, m01, v0), v1)                               # (ab).c1 = a0 b1 + a1 b0
+    k = tgt[0]; Cv[k] = ld2(g, "c", k); outs[k] = w2_redc(g, w2_addhi(g, x, Cv[k])); st2(g, "o", k, outs[k])
+    A[2] = ld2(g, "a", 2)
+    t = f2_mulw(g, A[2], Bv[0])
+    x = w2_add(g, t, v1)                                                # (ab).c2 = a1 b1 + a2 b0
+    if kind == "vadd":
+        x = g.mul_xi(*x)
+    k = tgt[1]; Cv[k] = ld2(g, "c", k); outs[k] = w2_redc(g, w2_addhi(g, x, Cv[k])); st2(g, "o", k, outs[k])
+    t = f2_mulw(g, A[2], Bv[1])
+    x = w2_add(g, g.mul_xi(*t), v0)                                     # (ab).c0 = a0 b0 + xi a2 b1
+    k = tgt[2]; Cv[k] = ld2(g, "c", k); outs[k] = w2_redc(g, w2_addhi(g, x, Cv[k])); st2(g, "o", k, outs[k])
+    z = (0, 0)
+
+    def ref(i):
+        ab = f6_mul_ref(case(A, i), case(Bv, i) + [z])
+        if kind == "vadd":
+            ab = [f2_xi_ref(ab[2]), ab[0], ab[1]]
+        c = case(Cv, i)
+        return [((ab[j][0] + c[j][0] * R) % P, (ab[j][1] + c[j][1] * R) % P) for j in range(3)]
+    expect(outs, ref)
+    return g, []
+
+
+def gen_f6mul01_add():
+    """o = c + a * (b0 + b1 v): Fp6 a, c and the Fp2 pair b in shared-memory slots, result stored to the slots at o (o may be c): 15 mulw + 6 redc"""
+    return gen_f6mul01_acc("add")
+
+
+def gen_f6mul01_vadd():
+    """o = c + v * a * (b0 + b1 v), as above (o must not overlap a, b or c): 15 mulw + 6 redc"""
+    return gen_f6mul01_acc("vadd")
+
+
+def gen_gs(xi):
+    g = Gen("lz_gs%d" % xi, 7 + xi)
+    a, b = ld2(g, "a", 0), ld2(g, "b", 0)
+
+    def sqrw(x):
+        re = g.mulw(g.add8(x[0], x[1]), g.fpsub(x[0], x[1]))
+        im = g.mulw(g.add8(x[0], x[0]), x[1])
+        return re, im
+
+    def tri(w):
+        return g.addw(g.dblw(w), w)
+    a2, b2 = sqrw(a), sqrw(b)
+    t0 = w2_add(g, g.mul_xi(*b2), a2)                                   # a^2 + xi b^2
+    ga = ld2(g, "ga", 0)
+    oa = w2_redc(g, w2_addhi(g, (tri(t0[0]), tri(t0[1])), f2_add8(g, ga, ga), -1))
+    s = (g.fpadd(a[0], b[0]), g.fpadd(a[1], b[1]))
+    s2 = sqrw(s)
+    t1 = w2_sub(g, w2_sub(g, s2, a2), b2)                               # 2 a b
+    if xi:
+        t1 = g.mul_xi(*t1)
+    gb = ld2(g, "gb", 0)
+    ob = w2_redc(g, w2_addhi(g, (tri(t1[0]), tri(t1[1])), f2_add8(g, gb, gb)))
+    st2(g, "oa", 0, oa); st2(g, "ob", 0, ob)
+    sq = lambda x: f2_mul_ref(x, x)
+
+    def ref(i):
+        av, bv, gav, gbv = case([a], i)[0], case([b], i)[0], case([ga], i)[0], case([gb], i)[0]
+        u0 = f2_add_ref(sq(av), f2_xi_ref(sq(bv)))
+        u1 = f2_mul_ref(f2_add_ref(av, av), bv)
+        if xi:
+            u1 = f2_xi_ref(u1)
+        return [tuple((3 * u0[j] - 2 * gav[j] * R) % P for j in range(2)), tuple((3 * u1[j] + 2 * gbv[j] * R) % P for j in range(2))]
+    expect([oa, ob], ref)
+    return g, []
+
+
+def gen_gs0():
+    """Granger-Scott step on one Fp4 pair: with (t0, t1) = (a^2 + xi b^2, 2 a b), slots oa <- 3 t0 - 2 ga, ob <- 3 t1 + 2 gb (stored at the end: oa, ob may be a, b, ga, gb): 6 mulw + 4 redc"""
+    return gen_gs(0)
+
+
+def gen_gs1():
+    """as lz_gs0 with ob <- 3 xi t1 + 2 gb"""
+    return gen_gs(1)
+
+
+VSIG_ACC = "uint32_t o, uint32_t a, uint32_t b, uint32_t c"
+VSIG_GS = "uint32_t a, uint32_t b, uint32_t ga, uint32_t gb, uint32_t oa, uint32_t ob"
 ROUTINES = [("lz_f6mul", gen_f6mul, "uint32_t a, uint32_t b", "fp6"), ("lz_f6mul01", gen_f6mul01, "uint32_t a, uint32_t b", "fp6"),
             ("lz_f4sqr", gen_f4sqr, "uint32_t a, uint32_t b", "fp4")]
+# Fused forms that were generated, bound-checked and COUNTED in round 2 but are not emitted (gen_lazy.py --experiments prints their
+# statistics): folding the accumulator into the wide domain (o = c + a b, o = c + v a b through n * 2^256 terms) and the Granger-Scott
+# combinations 3 t -+ 2 g push the unreduced values past 4 p 2^256, and the conditional subtractions that brings back (csubw: 9 for the
+# v-form against 2, 16 - 30 for a Granger-Scott pair against 2) cost more instructions than the narrow modular additions they replace.
+EXPERIMENTS = [("lz_f6mul01_add", gen_f6mul01_add, VSIG_ACC, None), ("lz_f6mul01_vadd", gen_f6mul01_vadd, VSIG_ACC, None),
+               ("lz_gs0", gen_gs0, VSIG_GS, None), ("lz_gs1", gen_gs1, VSIG_GS, None)]
 
 HEADER = """// GENERATED by tools/gen_lazy.py (bounds proved on exact linear forms, values checked on random and extreme inputs). Do not edit.
 // Lazily reduced Fp6-level routines of the BN254 tower over operands in shared-memory slots: the 512-bit products of a routine are
@@ -430,6 +563,9 @@ def render(verbose=False):
         g, outs = fn()
         if verbose:
             print("%-12s %s" % (name, g.stats))
+        if rtype is None:
+            out.append("// %s\nLZ_FN void %s(%s) {\n%s\n}\n" % (fn.__doc__.strip().split("\n")[0], name, sig, g.body()))
+            continue
         ret = "\n".join("    for (int i_ = 0; i_ < 8; i_++) { r_.c%d.c0.v[i_] = %s[i_]; r_.c%d.c1.v[i_] = %s[i_]; }" % (k, re.name, k, im.name)
                         for k, (re, im) in enumerate(outs))
         out.append("// %s\nLZ_FN %s %s(%s) {\n%s\n    %s r_;\n%s\n    return r_;\n}\n" % (fn.__doc__.strip().split("\n")[0], rtype, name, sig, g.body(), rtype, ret))
@@ -438,6 +574,10 @@ def render(verbose=False):
 
 def main():
     text = render(verbose=True)
+    if "--experiments" in sys.argv:
+        for name, fn, sig, rtype in EXPERIMENTS:
+            g, outs = fn()
+            print("%-16s %s" % (name, g.stats))
     if "--check" in sys.argv:
         return
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

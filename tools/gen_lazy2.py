@@ -1,0 +1,463 @@
+#!/usr/bin/env python3
+"""Lazy-reduction compiler for the TWO-LANES-PER-PROOF layout (writes csrc/lazy2_gen.cuh).
+
+VERDICT round 1 asked for a measured alternative to one proof per thread: here two adjacent lanes of a warp share one proof.  Lane 0
+owns the real component of every Fp2 value, lane 1 the imaginary one; both lanes execute ONE instruction stream (no divergence) whose
+operands are picked by lane parity:
+
+    (x0 + x1 u)(y0 + y1 u):   lane 0: x0 y0 + x1 (k p - y1)      lane 1: x0 y1 + x1 y0
+    (x0 + x1 u)^2:            lane 0: (x0 + x1)(x0 - x1)          lane 1: (2 x0) x1
+
+i.e. schoolbook over Fp2 as ONE 128-IMAD.WIDE accumulation chain per lane (lz_mulw2: a b + c d, no wide addition, no Karatsuba
+recombination), Karatsuba only at the Fp6 level, one Montgomery reduction per output component.  Against the one-thread routines of
+tools/gen_lazy.py a sparse Fp6 product costs 2 x 856 instead of 1392 IMAD.WIDE (+23 %) but about a third of the additions, half the live
+registers per lane (so four warps per scheduler instead of two) and a fifth of the code.  The only cross-lane traffic is the
+multiplication by xi = 9 + u of an unreduced value (16 shuffles).
+
+Bookkeeping is the one of gen_lazy.py, done for both lanes at once: every value carries, PER LANE, its exact expression as an integer
+linear combination of products of the routine's inputs and concrete values on random / extreme inputs; offsets and conditional
+subtractions are chosen for the worse lane, so the emitted stream is the same for both.  Results are checked against plain modular arithmetic.
+
+Usage: gen_lazy2.py [--check]
+"""
+import os
+import random
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import gen_lazy as GL
+from gen_lazy import P, R, RINV, BW, LIM, UNIT, NCASE, Atom, lin_add, limbs, f2_mul_ref, f2_add_ref, f2_xi_ref, f6_mul_ref
+
+ONE = Atom("1", 2, [1] * NCASE)          # the constant 1, so that k p - x has an exact linear form
+
+
+def kmax(k):
+    return (k[0].hi - 1) * (k[1].hi - 1) if len(k) == 2 else k[0].hi - 1
+
+
+def n_hi(lin):
+    return sum(c * (a.hi - 1) for a, c in lin.items() if c > 0)
+
+
+def n_lo(lin):
+    return sum(c * (a.hi - 1) for a, c in lin.items() if c < 0)
+
+
+def w_hi(lin, off):
+    return off + sum(c * kmax(k) for k, c in lin.items() if c > 0)
+
+
+def w_lo(lin, off):
+    return off + sum(c * kmax(k) for k, c in lin.items() if c < 0)
+
+
+class N2:
+    """narrow value (8 limbs) of both lanes: lin[l], vals[l] for lane l"""
+    def __init__(self, name, lin, vals, canon=False):
+        self.name, self.lin, self.vals, self.canon = name, lin, vals, canon
+
+    def hi(self):
+        return max(n_hi(l) for l in self.lin)
+
+
+class W2:
+    """wide value (16 limbs) of both lanes; the constant offset is common (it is an emitted literal)"""
+    def __init__(self, name, lin, off, vals):
+        self.name, self.lin, self.off, self.vals = name, lin, off, vals
+
+    def hi(self):
+        return max(w_hi(l, self.off) for l in self.lin)
+
+    def lo(self):
+        return min(w_lo(l, self.off) for l in self.lin)
+
+
+class Gen2:
+    def __init__(self, name, seed=1):
+        self.name, self.lines, self.nid = name, [], 0
+        self.rnd = random.Random(0xB2002 ^ seed)
+        self.stats = {"mulw": 0, "mulw2": 0, "redc": 0, "csubw": 0, "csub8": 0, "addhi": 0, "wide_addsub": 0, "narrow": 0, "sel": 0, "xchg": 0}
+
+    def emit(self, s):
+        self.lines.append(s)
+
+    def _n(self, lin, vals, canon=False):
+        self.nid += 1
+        name = "n%d" % self.nid
+        self.lines.append("uint32_t %s[8];" % name)
+        for l in range(2):
+            assert n_lo(lin[l]) >= 0 or all(v >= 0 for v in vals[l])
+            for v in vals[l]:
+                assert 0 <= v < R, "narrow overflow in %s" % self.name
+            assert n_hi(lin[l]) < R, "narrow bound in %s" % self.name
+        return N2(name, lin, vals, canon)
+
+    def _w(self, lin, off, vals):
+        self.nid += 1
+        name = "w%d" % self.nid
+        self.lines.append("uint32_t %s[16];" % name)
+        w = W2(name, lin, off, vals)
+        assert w.lo() >= 0 and w.hi() < LIM, "wide bound violated in %s: [%d, %.3f B]" % (self.name, w.lo(), w.hi() / BW)
+        for l in range(2):
+            for v in vals[l]:
+                assert w_lo(lin[l], off) <= v <= w_hi(lin[l], off), "bound engine disagrees with a concrete value in %s" % self.name
+        return w
+
+    def atom_vals(self, hi):
+        vals = [hi - 1, 0]
+        while len(vals) < NCASE:
+            m = self.rnd.random()
+            vals.append(hi - 1 if m < 0.25 else 0 if m < 0.35 else 1 if m < 0.4 else self.rnd.randrange(hi))
+        return vals
+
+    # ---- operands in shared-memory slots: an Fp2 operand k of `base` has its components in slots 2k, 2k+1
+    def operand(self, base, k):
+        """declare the Fp2 operand (two canonical atoms); returns a handle for ld_*"""
+        return (base, k, Atom("%s%d.re" % (base, k), P, self.atom_vals(P)), Atom("%s%d.im" % (base, k), P, self.atom_vals(P)))
+
+    def ld_fixed(self, opnd, comp):
+        base, k, re, im = opnd
+        a = (re, im)[comp]
+        v = self._n([{a: 1}, {a: 1}], [list(a.vals), list(a.vals)], True)
+        self.emit("lz_ld(%s, %s + %d * LZ_SLOT);" % (v.name, base, 2 * k + comp))
+        return v
+
+    def ld_own(self, opnd, other=False):
+        """lane 0 loads the real component, lane 1 the imaginary one (other=True: the other way round)"""
+        base, k, re, im = opnd
+        a = (im, re) if other else (re, im)
+        v = self._n([{a[0]: 1}, {a[1]: 1}], [list(a[0].vals), list(a[1].vals)], True)
+        self.emit("lz_ld(%s, %s + %d * LZ_SLOT + %s);" % (v.name, base, 2 * k, "oth" if other else "own"))
+        return v
+
+    def st_own(self, base, k, v):
+        assert v.canon
+        self.emit("lz_st(%s + %d * LZ_SLOT + own, %s);" % (base, 2 * k, v.name))
+
+    # ---- narrow
+    def add8(self, a, b):
+        self.stats["narrow"] += 1
+        v = self._n([lin_add(a.lin[l], b.lin[l]) for l in range(2)], [[x + y for x, y in zip(a.vals[l], b.vals[l])] for l in range(2)])
+        self.emit("lz_add8(%s, %s, %s);" % (v.name, a.name, b.name))
+        return v
+
+    def comp(self, a):
+        """p - a for a canonical a: a representative of -a in [1, p].  It becomes a fresh atom, so that sums of complements stay linear
+        forms with non-negative coefficients and the Karatsuba cancellations (x0 + x0')(c + c') - x0 c - x0' c' >= 0 remain KNOWN."""
+        assert a.canon
+        self.stats["narrow"] += 1
+        vals = [[P - x for x in a.vals[l]] for l in range(2)]
+        ats = [Atom("c", P + 1, vals[l]) for l in range(2)]
+        v = self._n([{ats[0]: 1}, {ats[1]: 1}], vals)
+        self.emit("{ const uint32_t k_[8] = {%s}; lz_sub8(%s, k_, %s); }" % (limbs(P, 8), v.name, a.name))
+        return v
+
+    def _modop(self, fn, pyf, *args):
+        for a in args:
+            assert a.canon
+        self.stats["narrow"] += 3
+        vals = [[pyf(*[a.vals[l][i] for a in args]) % P for i in range(NCASE)] for l in range(2)]
+        ats = [Atom("m", P, vals[l]) for l in range(2)]
+        v = self._n([{ats[0]: 1}, {ats[1]: 1}], vals, True)
+        self.emit("%s(%s, %s);" % (fn, v.name, ", ".join(a.name for a in args)))
+        return v
+
+    def fpadd(self, a, b): return self._modop("fp_add_ptx", lambda x, y: x + y, a, b)
+    def fpsub(self, a, b): return self._modop("fp_sub_ptx", lambda x, y: x - y, a, b)
+
+    def sel(self, x, y):
+        """lane 0 takes x, lane 1 takes y"""
+        self.stats["sel"] += 1
+        v = self._n([x.lin[0], y.lin[1]], [x.vals[0], y.vals[1]], x.canon and y.canon)
+        self.emit("lz_sel8(%s, %s, %s, im);" % (v.name, x.name, y.name))
+        return v
+
+    # ---- wide
+    @staticmethod
+    def _prod(la, lb):
+        lin = {}
+        for ka, ca in la.items():
+            for kb, cb in lb.items():
+                key = (ka, kb) if id(ka) <= id(kb) else (kb, ka)
+                lin[key] = lin.get(key, 0) + ca * cb
+        return {k: c for k, c in lin.items() if c}
+
+    def mulw(self, a, b):
+        self.stats["mulw"] += 1
+        w = self._w([self._prod(a.lin[l], b.lin[l]) for l in range(2)], 0, [[x * y for x, y in zip(a.vals[l], b.vals[l])] for l in range(2)])
+        self.emit("lz_mulw(%s, %s, %s);" % (w.name, a.name, b.name))
+        return w
+
+    def mulw2(self, a, b, c, d):
+        """a b + c d in one accumulation chain"""
+        self.stats["mulw2"] += 1
+        w = self._w([lin_add(self._prod(a.lin[l], b.lin[l]), self._prod(c.lin[l], d.lin[l])) for l in range(2)], 0,
+                    [[x * y + z * t for x, y, z, t in zip(a.vals[l], b.vals[l], c.vals[l], d.vals[l])] for l in range(2)])
+        self.emit("lz_mulw2(%s, %s, %s, %s, %s);" % (w.name, a.name, b.name, c.name, d.name))
+        return w
+
+    def csub(self, x, k):
+        self.stats["csubw"] += 1
+        assert 1 <= k <= 4 and x.lo() >= 0
+        hi = max(k * BW - 1, x.hi() - k * BW)
+        vals = [[v - k * BW if v >= k * BW else v for v in x.vals[l]] for l in range(2)]
+        self.nid += 1
+        ats = [Atom("cs%d" % self.nid, hi + 1, vals[l]) for l in range(2)]
+        w = self._w([{(ats[0],): 1}, {(ats[1],): 1}], 0, vals)
+        self.emit("{ const uint32_t k_[8] = {%s}; lz_csubw(%s, %s, k_); }" % (limbs(k * P, 8), w.name, x.name))
+        return w
+
+    def ensure(self, x, limit):
+        while x.hi() > limit:
+            k = 4
+            while k > 1 and k * BW > x.hi() - limit and k * BW - 1 > limit:
+                k //= 2
+            while k * BW > x.hi():
+                k //= 2
+            assert k >= 1, "cannot reduce below the limit"
+            x = self.csub(x, k)
+        return x
+
+    def addoff(self, x, off):
+        assert off % UNIT == 0 and off > 0
+        self.stats["addhi"] += 1
+        x = self.ensure(x, LIM - 1 - off)
+        w = self._w(x.lin, x.off + off, [[v + off for v in x.vals[l]] for l in range(2)])
+        self.emit("{ const uint32_t c_[9] = {%s}; lz_addhi(%s, %s, c_); }" % (limbs(off >> 224, 9), w.name, x.name))
+        return w
+
+    def addw(self, a, b):
+        self.stats["wide_addsub"] += 1
+        while a.hi() + b.hi() >= LIM:
+            if a.hi() >= b.hi():
+                a = self.ensure(a, max(BW - 1, a.hi() // 2))
+            else:
+                b = self.ensure(b, max(BW - 1, b.hi() // 2))
+        w = self._w([lin_add(a.lin[l], b.lin[l]) for l in range(2)], a.off + b.off, [[x + y for x, y in zip(a.vals[l], b.vals[l])] for l in range(2)])
+        self.emit("lz_addw(%s, %s, %s);" % (w.name, a.name, b.name))
+        return w
+
+    def subw(self, a, b):
+        self.stats["wide_addsub"] += 1
+        while True:
+            lins = [lin_add(a.lin[l], b.lin[l], -1) for l in range(2)]
+            lo = min(w_lo(lins[l], a.off - b.off) for l in range(2))
+            if lo >= 0:
+                break
+            a = self.addoff(a, -(lo // UNIT) * UNIT)
+        w = self._w(lins, a.off - b.off, [[x - y for x, y in zip(a.vals[l], b.vals[l])] for l in range(2)])
+        self.emit("lz_subw(%s, %s, %s);" % (w.name, a.name, b.name))
+        return w
+
+    def dblw(self, a):
+        a = self.ensure(a, LIM // 2 - 1)
+        self.stats["wide_addsub"] += 1
+        w = self._w([{k: 2 * c for k, c in a.lin[l].items()} for l in range(2)], 2 * a.off, [[2 * v for v in a.vals[l]] for l in range(2)])
+        self.emit("lz_addw(%s, %s, %s);" % (w.name, a.name, a.name))
+        return w
+
+    def mul9(self, x):
+        return self.addw(self.dblw(self.dblw(self.dblw(x))), x)
+
+    def xchg(self, x):
+        """the other lane's copy of a wide value (16 shuffles)"""
+        self.stats["xchg"] += 1
+        w = self._w([x.lin[1], x.lin[0]], x.off, [x.vals[1], x.vals[0]])
+        self.emit("lz_xchgw(%s, %s);" % (w.name, x.name))
+        return w
+
+    def selw_comp(self, x, k):
+        """lane 0: k p 2^256-multiple offset minus x (a non-negative representative of -x), lane 1: x.  Used by mul_xi.
+        Emitted as  t = OFF - x ; r = im ? x : t  with OFF the smallest multiple of p 2^224 that is >= hi(x)."""
+        off = -(-x.hi() // UNIT) * UNIT
+        self.stats["wide_addsub"] += 1
+        self.stats["sel"] += 2
+        neg_lin = [{kk: -c for kk, c in x.lin[l].items()} for l in range(2)]
+        # lane 0 holds off - x (constant offset off - x.off on top of -lin), lane 1 holds x: the offsets differ per lane, so the result is
+        # opaque from here on (fresh atoms with the right bounds): fine, it is only ever added to something
+        vals = [[off - v for v in x.vals[0]], list(x.vals[1])]
+        hi = max(off - w_lo(x.lin[0], x.off), w_hi(x.lin[1], x.off))
+        self.nid += 1
+        ats = [Atom("ng%d" % self.nid, hi + 1, vals[l]) for l in range(2)]
+        w = self._w([{(ats[0],): 1}, {(ats[1],): 1}], 0, vals)
+        self.emit("{ const uint32_t c_[16] = {%s}; lz_negsel(%s, %s, c_, im); }" % (limbs(off, 16), w.name, x.name))
+        return w, off
+
+    def mul_xi(self, x):
+        """own component of (9 + u)(re + im u): lane 0: 9 re - im, lane 1: 9 im + re, where the second term is the OTHER lane's value.
+        Lane 0 adds a multiple of p 2^224 minus the other value, so the stream is the same for both.  The result is opaque."""
+        t9 = self.mul9(x)
+        o = self.xchg(x)
+        s, off = self.selw_comp(o, 0)
+        return self.addw(t9, s)
+
+    def redc(self, x):
+        self.stats["redc"] += 1
+        x = self.ensure(x, 4 * BW - 1)
+        vals = [[(v * RINV) % P for v in x.vals[l]] for l in range(2)]
+        self.nid += 1
+        name = "n%d" % self.nid
+        self.lines.append("uint32_t %s[8];" % name)
+        self.emit("lz_redc(%s, %s);" % (name, x.name))
+        hi = (x.hi() >> 256) + P
+        assert hi < R
+        k = 4
+        while k >= 1:
+            if hi >= k * P:
+                self.stats["csub8"] += 1
+                self.emit("{ const uint32_t k_[8] = {%s}; lz_csub8(%s, %s, k_); }" % (limbs(k * P, 8), name, name))
+                hi = max(k * P - 1, hi - k * P)
+            k //= 2
+        assert hi < P
+        ats = [Atom("r%d" % self.nid, P, vals[l]) for l in range(2)]
+        return N2(name, [{ats[0]: 1}, {ats[1]: 1}], vals, True)
+
+    def body(self):
+        return "\n".join("    " + l for l in self.lines)
+
+
+# ------------------------------------------------------------------------------------------------------ building blocks
+class Op2:
+    """an Fp2 multiplicand prepared once per routine: x0, x1 as both lanes see them, and for a RIGHT operand the lane-selected pair
+    (t1, t2) = lane 0: (y0, k p - y1), lane 1: (y1, y0)"""
+    pass
+
+
+def left(g, X):
+    """X = (re, im) narrow values identical in both lanes (fixed loads or sums of them)"""
+    o = Op2(); o.x0, o.x1 = X
+    return o
+
+
+def right(g, own, oth, negoth):
+    """own / other component per lane and the complement of the other one (sums of such for the Karatsuba cross terms)"""
+    o = Op2()
+    o.t1 = own                                   # lane 0: y0, lane 1: y1
+    o.t2 = g.sel(negoth, oth)                    # lane 0: -y1 (as k p - y1), lane 1: y0
+    return o
+
+
+def f2_mulw(g, L, Rr):
+    """own component of the Fp2 product: one 128-IMAD.WIDE chain"""
+    return g.mulw2(L.x0, Rr.t1, L.x1, Rr.t2)
+
+
+def check(outs, ref, what):
+    """outs: list of N2 (own components of Fp2 results); ref(i) -> list of (re, im) integers without the Montgomery factor"""
+    for i in range(NCASE):
+        want = ref(i)
+        for o, (wr, wi) in zip(outs, want):
+            assert o.vals[0][i] == wr * RINV % P and o.vals[1][i] == wi * RINV % P, "value mismatch in " + what
+            assert o.canon
+
+
+def vals2(opnds, i):
+    return [(o[2].vals[i], o[3].vals[i]) for o in opnds]
+
+
+# ------------------------------------------------------------------------------------------------------ routines
+def gen_f6mul01():
+    """own components of a * (b0 + b1 v): Fp6 a and the Fp2 pair b in shared-memory slots, returned in registers: per lane 5 mulw2 + 3 redc"""
+    g = Gen2("lz2_f6mul01", 1)
+    A = [g.operand("a", k) for k in range(3)]
+    B = [g.operand("b", k) for k in range(2)]
+    a = [(g.ld_fixed(A[k], 0), g.ld_fixed(A[k], 1)) for k in range(2)]
+    bo = [(g.ld_own(B[k]), g.ld_own(B[k], True)) for k in range(2)]
+    nb = [g.comp(bo[k][1]) for k in range(2)]
+    rb = [right(g, bo[k][0], bo[k][1], nb[k]) for k in range(2)]
+    v0 = f2_mulw(g, left(g, a[0]), rb[0])
+    v1 = f2_mulw(g, left(g, a[1]), rb[1])
+    s01 = (g.add8(a[0][0], a[1][0]), g.add8(a[0][1], a[1][1]))
+    bs = right(g, g.add8(bo[0][0], bo[1][0]), g.add8(bo[0][1], bo[1][1]), g.add8(nb[0], nb[1]))
+    m01 = f2_mulw(g, left(g, s01), bs)
+    o1 = g.redc(g.subw(g.subw(m01, v0), v1))                                 # c1 = a0 b1 + a1 b0
+    a2 = (g.ld_fixed(A[2], 0), g.ld_fixed(A[2], 1))
+    t = f2_mulw(g, left(g, a2), rb[0])
+    o2 = g.redc(g.addw(t, v1))                                               # c2 = a1 b1 + a2 b0
+    t = f2_mulw(g, left(g, a2), rb[1])
+    o0 = g.redc(g.addw(g.mul_xi(t), v0))                                     # c0 = a0 b0 + xi a2 b1
+    z = (0, 0)
+    check([o0, o1, o2], lambda i: f6_mul_ref(vals2(A, i), vals2(B, i) + [z]), "f6mul01")
+    return g, [o0, o1, o2]
+
+
+def gen_f6mul():
+    """own components of a * b for two Fp6 operands in shared-memory slots, returned in registers: per lane 6 mulw2 + 3 redc"""
+    g = Gen2("lz2_f6mul", 2)
+    A = [g.operand("a", k) for k in range(3)]
+    B = [g.operand("b", k) for k in range(3)]
+    a = [(g.ld_fixed(A[k], 0), g.ld_fixed(A[k], 1)) for k in range(3)]
+    bo = [(g.ld_own(B[k]), g.ld_own(B[k], True)) for k in range(3)]
+    nb = [g.comp(bo[k][1]) for k in range(3)]
+    rb = [right(g, bo[k][0], bo[k][1], nb[k]) for k in range(3)]
+    v = [f2_mulw(g, left(g, a[k]), rb[k]) for k in range(3)]
+
+    def cross(i, j):
+        s = (g.add8(a[i][0], a[j][0]), g.add8(a[i][1], a[j][1]))
+        bs = right(g, g.add8(bo[i][0], bo[j][0]), g.add8(bo[i][1], bo[j][1]), g.add8(nb[i], nb[j]))
+        return g.subw(g.subw(f2_mulw(g, left(g, s), bs), v[i]), v[j])        # a_i b_j + a_j b_i
+    o1 = g.redc(g.addw(cross(0, 1), g.mul_xi(v[2])))                         # c1 = a0 b1 + a1 b0 + xi a2 b2
+    o2 = g.redc(g.addw(cross(0, 2), v[1]))                                   # c2 = a0 b2 + a2 b0 + a1 b1
+    o0 = g.redc(g.addw(g.mul_xi(cross(1, 2)), v[0]))                         # c0 = a0 b0 + xi (a1 b2 + a2 b1)
+    check([o0, o1, o2], lambda i: f6_mul_ref(vals2(A, i), vals2(B, i)), "f6mul")
+    return g, [o0, o1, o2]
+
+
+def gen_f4sqr():
+    """own components of (t0, t1) = (a^2 + xi b^2, 2 a b) for a + b s in Fp4, a and b Fp2 operands in slots; returned in registers: per lane 3 mulw + 2 redc"""
+    g = Gen2("lz2_f4sqr", 3)
+    A, B = g.operand("a", 0), g.operand("b", 0)
+    a = (g.ld_fixed(A, 0), g.ld_fixed(A, 1)); b = (g.ld_fixed(B, 0), g.ld_fixed(B, 1))
+
+    def sqrw(x):
+        """own component of (x0 + x1 u)^2: lane 0 (x0 + x1)(x0 - x1), lane 1 (2 x0) x1"""
+        s = g.sel(g.add8(x[0], x[1]), g.add8(x[0], x[0]))
+        t = g.sel(g.fpsub(x[0], x[1]), x[1])
+        return g.mulw(s, t)
+    a2, b2 = sqrw(a), sqrw(b)
+    r0 = g.redc(g.addw(g.mul_xi(b2), a2))
+    s = (g.fpadd(a[0], b[0]), g.fpadd(a[1], b[1]))
+    s2 = sqrw(s)
+    r1 = g.redc(g.subw(g.subw(s2, a2), b2))
+    sq = lambda x: f2_mul_ref(x, x)
+    check([r0, r1], lambda i: [f2_add_ref(sq(vals2([A], i)[0]), f2_xi_ref(sq(vals2([B], i)[0]))),
+                               f2_mul_ref(f2_add_ref(vals2([A], i)[0], vals2([A], i)[0]), vals2([B], i)[0])], "f4sqr")
+    return g, [r0, r1]
+
+
+ROUTINES = [("lz2_f6mul01", gen_f6mul01, "uint32_t a, uint32_t b"), ("lz2_f6mul", gen_f6mul, "uint32_t a, uint32_t b"),
+            ("lz2_f4sqr", gen_f4sqr, "uint32_t a, uint32_t b")]
+
+HEADER = """// GENERATED by tools/gen_lazy2.py (two lanes per proof; bounds proved per lane on exact linear forms, values checked on random and extreme
+// inputs for both lanes). Do not edit.  Lane parity `im` = threadIdx.x & 1 owns the real (0) or imaginary (1) component of every Fp2 value;
+// own = im * LZ_SLOT, oth = LZ_SLOT - own are slot offsets of the lane's own / the other component.  One instruction stream for both lanes.
+// This is the arithmetic behind the reference's ecPairing precompile call (/root/reference/contracts/src/common/groth16.rs:121-125).
+#pragma once
+"""
+
+
+def render(verbose=False):
+    out = [HEADER]
+    for name, fn, sig in ROUTINES:
+        g, outs = fn()
+        if verbose:
+            print("%-12s %s" % (name, g.stats))
+        rtype = "lz2_r%d" % len(outs)
+        ret = "\n".join("    for (int i_ = 0; i_ < 8; i_++) r_.c[%d].v[i_] = %s[i_];" % (k, o.name) for k, o in enumerate(outs))
+        out.append("// %s\nLZ_FN %s %s(%s, uint32_t own, uint32_t oth, uint32_t im) {\n%s\n    %s r_;\n%s\n    return r_;\n}\n"
+                   % (fn.__doc__.strip().split("\n")[0], rtype, name, sig, g.body(), rtype, ret))
+    return "\n".join(out)
+
+
+def main():
+    text = render(verbose=True)
+    if "--check" in sys.argv:
+        return
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "stylus_zkvm_verifiers_b200/csrc/lazy2_gen.cuh"), "w") as f:
+        f.write(text)
+    print("wrote lazy2_gen.cuh")
+
+
+if __name__ == "__main__":
+    main()

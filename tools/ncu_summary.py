@@ -15,7 +15,7 @@ WANT = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
         "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fmalite_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fmaheavy.sum", "sm__inst_executed_pipe_fmalite.sum",
         "sm__inst_executed_pipe_alu.sum", "sm__inst_executed.sum", "sm__cycles_active.avg", "launch__shared_mem_per_block_dynamic"]
-HEAVY = ("k_miller", "k_miller_norm", "k_final_exp", "k_miller_lz", "k_final_exp_lz", "k_miller_norm_seg", "k_final_exp_stage", "k_lz", "k_old", "k_pairing_lz")
+HEAVY = ("k_miller", "k_miller_norm", "k_final_exp", "k_miller_lz", "k_final_exp_lz", "k_miller_norm_seg", "k_final_exp_stage", "k_lz", "k_lz2", "k_old", "k_pairing_lz")
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
