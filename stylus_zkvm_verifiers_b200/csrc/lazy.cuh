@@ -396,14 +396,7 @@ LZ_FN2 void lz_frob(uint32_t a, int k) {
         if (i || (k & 1)) lz_st2(s, c);
     }
 }
-LZ_FN fp fpv_inv(fp a) {            // a^(p-2); inv(0) = 0
-    fp acc = fp_one();
-    for (int i = 253; i >= 0; i--) {
-        fp_sqr(acc, acc);
-        if ((C_PM2[i >> 5] >> (i & 31)) & 1) fp_mul(acc, acc, a);
-    }
-    return acc;
-}
+LZ_INL fp fpv_inv(fp a) { fp r; fp_inv(r, a); return r; }            // safegcd inversion of bn254.cuh; inv(0) = 0
 // A <- 1 / A in place (bn254.cuh f12_inv / f6_inv); x, y = Fp6 temporaries
 LZ_FN2 void lz_f12inv(uint32_t a, uint32_t x, uint32_t y) {
     LZ_RDV();

@@ -12,6 +12,7 @@ static void dec_f12(fp12& a, const uint8_t* in) { fp* w = &a.c0.c0.c0; for (int 
 extern "C" {
 int emu_fp_mul(const uint8_t* a, const uint8_t* b, uint8_t* out) { fp x, y, z; dec_fp(x, a); dec_fp(y, b); fp_mul(z, x, y); fp_to_be32(out, z); return 0; }
 int emu_fp_inv(const uint8_t* a, uint8_t* out) { fp x, z; dec_fp(x, a); fp_inv(z, x); fp_to_be32(out, z); return 0; }
+int emu_fp_inv_fermat(const uint8_t* a, uint8_t* out) { fp x, z; dec_fp(x, a); fp_inv_fermat(z, x); fp_to_be32(out, z); return 0; }
 int emu_f12_mul(const uint8_t* a, const uint8_t* b, uint8_t* out) { fp12 x, y, z; dec_f12(x, a); dec_f12(y, b); f12_mul(z, x, y); f12_to_bytes(out, z); return 0; }
 int emu_f12_sqr(const uint8_t* a, uint8_t* out) { fp12 x, z; dec_f12(x, a); f12_sqr(z, x); f12_to_bytes(out, z); return 0; }
 int emu_f12_cyc_sqr(const uint8_t* a, uint8_t* out) { fp12 x, z; dec_f12(x, a); f12_cyc_sqr(z, x); f12_to_bytes(out, z); return 0; }

@@ -60,6 +60,19 @@ def test_fp_and_fp12_ops(emu):
         assert O.fp12_mul(x, inv) == one
 
 
+def test_safegcd_inversion_equals_fermat_and_pow(emu):
+    """fp_inv (constant-time safegcd, 20 x 30 division steps) against the Fermat inversion it replaced and Python's pow, on edge values
+    (0 -> 0, 1, p - 1, small, powers of two, values around 2^k) and random ones."""
+    rng = SplitMix64(77)
+    out, ref = C.create_string_buffer(32), C.create_string_buffer(32)
+    vals = [0, 1, 2, 3, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, 1 << 253, (1 << 253) - 1, (1 << 128), (1 << 128) + 1, (1 << 30), (1 << 30) - 1, (1 << 60) + 5]
+    vals += [(1 << k) % P for k in range(0, 256, 17)] + [rng.fr() % P for _ in range(400)]
+    for a in vals:
+        emu.emu_fp_inv(w32(a), out); emu.emu_fp_inv_fermat(w32(a), ref)
+        want = pow(a, -1, P) if a else 0
+        assert out.raw[:32] == w32(want) == ref.raw[:32], hex(a)
+
+
 def test_final_exp_and_cyclotomic(emu):
     rng = SplitMix64(12)
     out = C.create_string_buffer(384)
