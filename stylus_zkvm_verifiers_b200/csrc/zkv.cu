@@ -266,7 +266,8 @@ extern "C" int zkv_vk_tune(const void* handle_vk, int option, int value) {
 // jo: offset of the first proof inside the job's buffers, o: offset inside the device workspace
 static const bool g_debug_sync = getenv("ZKV_DEBUG_SYNC") != nullptr;      // diagnostics: synchronise after every kernel of a chain and name the one that failed
 #define DBG(name) do { if (g_debug_sync) { cudaError_t e_ = cudaStreamSynchronize(s); if (e_ != cudaSuccess) return fail(ZKV_ERR_CUDA, std::string(name) + ": " + cudaGetErrorString(e_)); } } while (0)
-static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cudaStream_t s, bool timed) {
+static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cudaStream_t s, bool timed, bool mono_kernels = false) {
+    const bool mono = timed || mono_kernels;      // one-launch Miller loop / final exponentiation (no segments, no stages); `timed` also records the per-stage events
     const zkv_vk* vk = j.vk;
     int ns = (j.mode == SIG_GENERIC) ? j.k : 2;
     uint32_t* scal = c->scal + o * (size_t)ns * 8;
@@ -309,14 +310,14 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
     a.vk_skip = (uint8_t)((c->h_vk.g2_inf[1] ? 2 : 0) | (c->h_vk.g2_inf[2] ? 4 : 0));
     const int top = ZKV_ATE_NAF_LEN - 2;    // digits top .. 0 of the loop
     if (lazy) {                             // shared-memory-resident kernels (lazy.cuh): segments when chunked, one launch otherwise
-        const int S = (segs > 1 && !timed) ? segs : 1;
+        const int S = (segs > 1 && !mono) ? segs : 1;
         for (int k = 0; k < S; k++) {
             int hi = top - (top + 1) * k / S, lo = top - (top + 1) * (k + 1) / S + 1;
             k_miller_lz<<<nblk(m, LZ_NT), LZ_NT, LZ_SMEM_BYTES, s>>>(m, a, flags, c->f + o, c->rst + o, c->sl + 4 * o, hi, lo, k == 0, k == S - 1);
             DBG("k_miller_lz");
         }
         nl += S - 1;
-    } else if (norm && segs > 1 && !timed) {      // a timed single chain (per-stage roofline pass, small batches) runs the one-kernel form
+    } else if (norm && segs > 1 && !mono) {      // a timed single chain (per-stage roofline pass, small batches) runs the one-kernel form
         const int S = segs;
         for (int k = 0; k < S; k++) {
             int hi = top - (top + 1) * k / S, lo = top - (top + 1) * (k + 1) / S + 1;
@@ -327,9 +328,9 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
     else k_miller<<<nblk(m, ZKV_HTPB), ZKV_HTPB, 0, s>>>(m, a, flags, c->f + o);
     if (timed) CK(cudaEventRecord(c->ev[4], s));
     if (vk->tune.layout.load()) {
-        if (stages && !timed) { for (int st = 0; st < 4; st++) k_final_exp_lz<<<nblk(m, LZ_NT), LZ_NT, LZ_SMEM_BYTES, s>>>(m, st, st, c->f + o, c->fes + 6 * o, flags, j.d_status + jo, nullptr, 0); nl += 3; }
+        if (stages && !mono) { for (int st = 0; st < 4; st++) k_final_exp_lz<<<nblk(m, LZ_NT), LZ_NT, LZ_SMEM_BYTES, s>>>(m, st, st, c->f + o, c->fes + 6 * o, flags, j.d_status + jo, nullptr, 0); nl += 3; }
         else k_final_exp_lz<<<nblk(m, LZ_NT), LZ_NT, LZ_SMEM_BYTES, s>>>(m, 0, 3, c->f + o, c->fes + 6 * o, flags, j.d_status + jo, nullptr, 0);
-    } else if (stages && !timed) {
+    } else if (stages && !mono) {
         for (int st = 0; st < 4; st++) k_final_exp_stage<<<nblk(m, ZKV_HTPB_FE), ZKV_HTPB_FE, 0, s>>>(m, st, c->f + o, c->fes + 5 * o, flags, j.d_status + jo);
         nl += 3;
     } else k_final_exp<<<nblk(m, ZKV_HTPB_FE), ZKV_HTPB_FE, 0, s>>>(m, c->f + o, flags, j.d_status + jo, nullptr, 0);
@@ -339,15 +340,21 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
     CK(cudaGetLastError());
     return 0;
 }
-// Chunks of a device batch.  Automatic (setting 0): half a wave of the heavy kernels each (2 resident blocks of 128 threads per SM, so half a
-// wave = SMs x 128 proofs), evened out: two chunks are co-resident at any time, the block scheduler back-fills one chunk's partial wave with
-// the other's blocks, and what a batch can lose at its end is half a wave whatever its size (2^16 proofs on 148 SMs: 4 chunks of 16 384;
-// 2^17: 7 chunks of 18 816 instead of 4 x 32 768, each of which would occupy a whole wave's slots for 86 % of a wave's work).
+// Chunks of a device batch.  Measured on B200 (tools/sweep_chunks.sh, profiles/r2_chunk_sweep.txt): kernel chains of several chunks running
+// side by side on different streams only pay when the batch is a small number of waves of the heavy kernels (2 resident blocks of 128
+// threads per SM: one wave = SMs x 256 proofs).  2^16 proofs are 1.73 waves: one chain pays for two full waves (35.0 ms), four half-wave
+// chunks whose segment / stage kernels back-fill each other's partial waves take 33.8 ms.  From about two waves on, one serial chain of
+// one-launch kernels is faster than any chunking (2^17: 68.4 against 69.2 ms, 2^18: 126 against 141 ms, 2^20: 504 against 612 ms, i.e. 2.08 M
+// against 1.71 M verifies/s): co-scheduled kernels of different stages take each other's block slots, and the light kernels (vk_x, the
+// G2 check) run at a fraction of their own occupancy between the heavy blocks.  Automatic (setting 0): half-wave chunks below two waves,
+// one chain above.  A positive setting forces that many chunks.
+static size_t wave_proofs_of(const DevCtx* c) { return (size_t)c->sms * 2 * ZKV_HTPB; }
 static int chunk_count(const DevCtx* c, size_t n, int setting) {
     if (n < (size_t)8192) return 1;
     if (setting >= 1) return setting;
-    const size_t half = (size_t)c->sms * ZKV_HTPB;
-    return (int)std::min<size_t>(64, std::max<size_t>(1, (n + half - 1) / half));
+    if (n >= 2 * wave_proofs_of(c)) return 1;
+    const size_t half = wave_proofs_of(c) / 2;
+    return (int)std::max<size_t>(1, (n + half - 1) / half);
 }
 // Fork `chunks` side streams off `main`, run fn(chunk_begin, chunk_len, stream) on them round-robin, join back into `main`.
 // Chunk boundaries are multiples of the heavy kernels' block size so no chunk carries a second partial block.
@@ -390,10 +397,15 @@ static int host_pipeline(DevCtx* c, const zkv_vk* vk, size_t m, size_t in_bytes,
     int chunks = chunk_count(c, m, vk->tune.overlap_chunks.load());
     size_t per = (m + chunks - 1) / chunks;
     per = (per + ZKV_HTPB - 1) / ZKV_HTPB * ZKV_HTPB;
+    // Large batches (automatic setting, one kernel chain): the KERNELS of the whole batch run back to back on the main stream, but the batch is
+    // still cut, at whole waves, into pieces whose packing, upload (side stream 0) and status download (side stream 1) overlap the kernels
+    // of the pieces before / after them: copy pipelining without co-scheduling kernels of different stages.
+    const bool piped = chunks == 1 && vk->tune.overlap_chunks.load() == 0 && m >= 2 * wave_proofs_of(c);
+    if (piped) per = wave_proofs_of(c) * std::min<size_t>(4, std::max<size_t>(1, m / wave_proofs_of(c) / 3));
     chunks = (int)((m + per - 1) / per);
     // pack(first, cnt, nullptr) returns the size of a chunk's block, so every chunk's region of the pinned staging buffer is known up front
-    // and the chunks can be packed by concurrent host threads: chunk 0 on this thread, the others on helpers that are joined right before
-    // their chunk is enqueued.  Packing is a handful of bulk memcpy per chunk, i.e. memory-bandwidth work.
+    // and the chunks can be packed by concurrent host threads: chunk 0 on this thread, the others on helpers.  Packing is a handful of bulk
+    // memcpy per chunk, i.e. memory-bandwidth work.
     std::vector<size_t> bytes(chunks, 0), offs(chunks + 1, 0);
     for (int k = 0; k < chunks; k++) { size_t first = per * (size_t)k; bytes[k] = pack(first, std::min(per, m - first), nullptr); offs[k + 1] = offs[k] + (bytes[k] + 255) / 256 * 256; }
     (void)in_bytes;
@@ -408,20 +420,30 @@ static int host_pipeline(DevCtx* c, const zkv_vk* vk, size_t m, size_t in_bytes,
         for (int k = h + 1; k < chunks; k += H) { size_t first = per * (size_t)k; pack(first, std::min(per, m - first), c->h_pin + offs[k]); ready[k].store(1, std::memory_order_release); }
     });
     pack(0, std::min(per, m), c->h_pin); ready[0].store(1);
+    std::vector<cudaEvent_t> evs;                    // piped: upload-done and chain-done events per piece
+    if (piped) { evs.resize(2 * (size_t)chunks, nullptr); for (auto& e : evs) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "cudaEventCreate"); }
     int used = 0;
     for (int k = 0; k < chunks && !rc; k++) {
         const size_t first = per * (size_t)k, cnt = std::min(per, m - first), in_off = offs[k];
         cudaStream_t s = chunks == 1 ? c->stream : c->aux[k % DevCtx::NAUX];
-        if (chunks > 1) used = std::max(used, k % DevCtx::NAUX + 1);
+        cudaStream_t s_in = piped ? c->aux[0] : s, s_out = piped ? c->aux[1] : s;
+        if (piped) { s = c->stream; used = 2; }
+        else if (chunks > 1) used = std::max(used, k % DevCtx::NAUX + 1);
         while (!ready[k].load(std::memory_order_acquire)) std::this_thread::yield();
-        rc = cudaMemcpyAsync(c->d_in + in_off, c->h_pin + in_off, bytes[k], cudaMemcpyHostToDevice, s) == cudaSuccess ? 0 : fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (host to device)");
-        if (!rc) { Job j = job(first, cnt, c->d_in + in_off); rc = enqueue_chain(c, j, 0, first, (int)cnt, s, chunks == 1); }
-        if (!rc && cudaMemcpyAsync(c->h_out + first, c->d_out + first, cnt, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (device to host)");
+        rc = cudaMemcpyAsync(c->d_in + in_off, c->h_pin + in_off, bytes[k], cudaMemcpyHostToDevice, s_in) == cudaSuccess ? 0 : fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (host to device)");
+        if (!rc && piped && (cudaEventRecord(evs[2 * k], s_in) != cudaSuccess || cudaStreamWaitEvent(s, evs[2 * k], 0) != cudaSuccess)) rc = fail(ZKV_ERR_CUDA, "event (upload done)");
+        if (!rc) { Job j = job(first, cnt, c->d_in + in_off); rc = enqueue_chain(c, j, 0, first, (int)cnt, s, chunks == 1, piped); }
+        if (!rc && piped && (cudaEventRecord(evs[2 * k + 1], s) != cudaSuccess || cudaStreamWaitEvent(s_out, evs[2 * k + 1], 0) != cudaSuccess)) rc = fail(ZKV_ERR_CUDA, "event (chain done)");
+        if (!rc && cudaMemcpyAsync(c->h_out + first, c->d_out + first, cnt, cudaMemcpyDeviceToHost, s_out) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (device to host)");
     }
     for (auto& t : helpers) t.join();
-    if (rc) { cudaDeviceSynchronize(); return rc; }
+    if (rc) { cudaDeviceSynchronize(); for (auto e : evs) if (e) cudaEventDestroy(e); return rc; }
     if (chunks == 1) { CK(cudaStreamSynchronize(c->stream)); collect_stage_ms(c); }
-    else for (int a = 0; a < used; a++) CK(cudaStreamSynchronize(c->aux[a]));
+    else {
+        for (int a = 0; a < used; a++) CK(cudaStreamSynchronize(c->aux[a]));
+        if (piped) CK(cudaStreamSynchronize(c->stream));
+    }
+    for (auto e : evs) if (e) cudaEventDestroy(e);
     return 0;
 }
 static void collect_stage_ms(DevCtx* c) {
