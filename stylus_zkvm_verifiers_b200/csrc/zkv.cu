@@ -266,36 +266,40 @@ extern "C" int zkv_vk_tune(const void* handle_vk, int option, int value) {
 // jo: offset of the first proof inside the job's buffers, o: offset inside the device workspace
 static const bool g_debug_sync = getenv("ZKV_DEBUG_SYNC") != nullptr;      // diagnostics: synchronise after every kernel of a chain and name the one that failed
 #define DBG(name) do { if (g_debug_sync) { cudaError_t e_ = cudaStreamSynchronize(s); if (e_ != cudaSuccess) return fail(ZKV_ERR_CUDA, std::string(name) + ": " + cudaGetErrorString(e_)); } } while (0)
-static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cudaStream_t s, bool timed, bool mono_kernels = false) {
+// phases: 1 = the front kernels (decode, public-input hashing, vk_x, G2 check), 2 = the heavy ones (Miller loop, final exponentiation), 3 = both
+static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cudaStream_t s, bool timed, bool mono_kernels = false, int phases = 3) {
     const bool mono = timed || mono_kernels;      // one-launch Miller loop / final exponentiation (no segments, no stages); `timed` also records the per-stage events
     const zkv_vk* vk = j.vk;
     int ns = (j.mode == SIG_GENERIC) ? j.k : 2;
     uint32_t* scal = c->scal + o * (size_t)ns * 8;
     uint8_t* flags = c->flags + o;
-    if (timed) CK(cudaEventRecord(c->ev[0], s));
-    k_decode<<<nblk(m), TPB, 0, s>>>(m, j.rec_off ? j.recs : j.recs + jo * j.stride, j.stride, j.off, j.selector_le, j.check_selector, vk->vm, j.rec_off ? j.rec_off + jo : nullptr, j.rec_base, c->px[0] + o, c->py[0] + o, c->qx + o, c->qy + o, c->px[3] + o, c->py[3] + o, flags);
-    const g1aff* tab = c->d_tab; int nwin = ZKV_WIN_PER_SCALAR;
-    switch (j.mode) {
-        case SIG_GENERIC: k_generic_signals<<<nblk(m), TPB, 0, s>>>(m, j.k, j.sig_a + jo * (size_t)j.k * 32, scal, flags); break;
-        case SIG_RISC0_VERIFY: k_risc0_signals<<<nblk(m), TPB, 0, s>>>(m, j.sig_a + jo * 32, j.sig_b + jo * 32, nullptr, 0, j.hc, scal); break;
-        case SIG_RISC0_INTEGRITY: k_risc0_signals<<<nblk(m), TPB, 0, s>>>(m, nullptr, nullptr, j.sig_a + jo * 32, 1, j.hc, scal); break;
-        case SIG_SP1: k_sp1_signals<<<nblk(m), TPB, 0, s>>>(m, j.sig_a + jo * 32, j.pv_off ? j.sig_b : j.sig_b + jo * j.pv_stride, j.pv_off ? j.pv_off + jo : nullptr, j.pv_base, j.pv_stride, scal, flags); break;
+    if (phases & 1) {
+        if (timed) CK(cudaEventRecord(c->ev[0], s));
+        k_decode<<<nblk(m), TPB, 0, s>>>(m, j.rec_off ? j.recs : j.recs + jo * j.stride, j.stride, j.off, j.selector_le, j.check_selector, vk->vm, j.rec_off ? j.rec_off + jo : nullptr, j.rec_base, c->px[0] + o, c->py[0] + o, c->qx + o, c->qy + o, c->px[3] + o, c->py[3] + o, flags);
+        const g1aff* tab = c->d_tab; int nwin = ZKV_WIN_PER_SCALAR;
+        switch (j.mode) {
+            case SIG_GENERIC: k_generic_signals<<<nblk(m), TPB, 0, s>>>(m, j.k, j.sig_a + jo * (size_t)j.k * 32, scal, flags); break;
+            case SIG_RISC0_VERIFY: k_risc0_signals<<<nblk(m), TPB, 0, s>>>(m, j.sig_a + jo * 32, j.sig_b + jo * 32, nullptr, 0, j.hc, scal); break;
+            case SIG_RISC0_INTEGRITY: k_risc0_signals<<<nblk(m), TPB, 0, s>>>(m, nullptr, nullptr, j.sig_a + jo * 32, 1, j.hc, scal); break;
+            case SIG_SP1: k_sp1_signals<<<nblk(m), TPB, 0, s>>>(m, j.sig_a + jo * 32, j.pv_off ? j.sig_b : j.sig_b + jo * j.pv_stride, j.pv_off ? j.pv_off + jo : nullptr, j.pv_base, j.pv_stride, scal, flags); break;
+        }
+        if (j.mode == SIG_RISC0_VERIFY || j.mode == SIG_RISC0_INTEGRITY) { tab = c->d_tab + (size_t)2 * ZKV_WIN_PER_SCALAR * ZKV_WIN_ENTRIES; nwin = 32; }   // claim_lo / claim_hi are 128-bit
+        if (timed) CK(cudaEventRecord(c->ev[1], s));
+        if (j.all_fail || !vk->valid) {
+            k_status_all_fail<<<nblk(m), TPB, 0, s>>>(m, flags, j.d_status + jo);
+            g_launches += 3;
+            if (timed) for (int e = 2; e < 6; e++) CK(cudaEventRecord(c->ev[e], s));
+            CK(cudaGetLastError());
+            return 0;
+        }
+        k_vkx<<<nblk(m), TPB, 0, s>>>(m, scal, ns, nwin, tab, j.base, c->px[2] + o, c->py[2] + o, flags);
+        if (timed) CK(cudaEventRecord(c->ev[2], s));
+        DBG("decode / signals / vk_x");
+        k_g2_check<<<nblk(m), TPB, 0, s>>>(m, c->qx + o, c->qy + o, flags);
+        DBG("k_g2_check");
+        if (timed) CK(cudaEventRecord(c->ev[3], s));
+        if (!(phases & 2)) { g_launches += 4; CK(cudaGetLastError()); return 0; }
     }
-    if (j.mode == SIG_RISC0_VERIFY || j.mode == SIG_RISC0_INTEGRITY) { tab = c->d_tab + (size_t)2 * ZKV_WIN_PER_SCALAR * ZKV_WIN_ENTRIES; nwin = 32; }   // claim_lo / claim_hi are 128-bit
-    if (timed) CK(cudaEventRecord(c->ev[1], s));
-    if (j.all_fail || !vk->valid) {
-        k_status_all_fail<<<nblk(m), TPB, 0, s>>>(m, flags, j.d_status + jo);
-        g_launches += 3;
-        if (timed) for (int e = 2; e < 6; e++) CK(cudaEventRecord(c->ev[e], s));
-        CK(cudaGetLastError());
-        return 0;
-    }
-    k_vkx<<<nblk(m), TPB, 0, s>>>(m, scal, ns, nwin, tab, j.base, c->px[2] + o, c->py[2] + o, flags);
-    if (timed) CK(cudaEventRecord(c->ev[2], s));
-    DBG("decode / signals / vk_x");
-    k_g2_check<<<nblk(m), TPB, 0, s>>>(m, c->qx + o, c->qy + o, flags);
-    DBG("k_g2_check");
-    if (timed) CK(cudaEventRecord(c->ev[3], s));
     MillerArgs a; memset(&a, 0, sizeof a);
     a.px[0] = c->px[0] + o; a.py[0] = c->py[0] + o; a.px[1] = c->px[2] + o; a.py[1] = c->py[2] + o; a.px[2] = c->px[3] + o; a.py[2] = c->py[3] + o;
     a.qx = c->qx + o; a.qy = c->qy + o;
@@ -305,7 +309,7 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
     const bool norm = c->h_vk.norm_ok && vk->tune.normalised_lines.load();
     const bool lazy = norm && vk->tune.layout.load();
     const int segs = vk->tune.miller_segments.load(), stages = vk->tune.final_exp_stages.load();
-    int nl = 4;                             // decode, signals, vk_x, G2 check
+    int nl = (phases & 1) ? 4 : 0;          // decode, signals, vk_x, G2 check
     a.skip_bit[0] = F_SKIP0; a.skip_bit[1] = F_SKIPX; a.skip_bit[2] = F_SKIPC;
     a.vk_skip = (uint8_t)((c->h_vk.g2_inf[1] ? 2 : 0) | (c->h_vk.g2_inf[2] ? 4 : 0));
     const int top = ZKV_ATE_NAF_LEN - 2;    // digits top .. 0 of the loop
@@ -381,7 +385,10 @@ static int run_verify(DevCtx* c, const Job& j) {
     rc = ctx_reserve(c, j.n, (size_t)ns * 8); if (rc) return rc;
     int chunks = chunk_count(c, j.n, j.vk->tune.overlap_chunks.load());
     if (chunks <= 1) return enqueue_chain(c, j, 0, 0, (int)j.n, c->stream, true);
-    return fork_join(c, c->stream, j.n, chunks, [&](size_t o, int m, cudaStream_t s) { return enqueue_chain(c, j, o, o, m, s, false); });
+    if (j.all_fail || !j.vk->valid) return enqueue_chain(c, j, 0, 0, (int)j.n, c->stream, false);
+    // the front kernels run once over the whole batch (at their own full occupancy), only the heavy kernels are chunked over the side streams
+    rc = enqueue_chain(c, j, 0, 0, (int)j.n, c->stream, false, false, 1); if (rc) return rc;
+    return fork_join(c, c->stream, j.n, chunks, [&](size_t o, int m, cudaStream_t s) { return enqueue_chain(c, j, o, o, m, s, false, false, 2); });
 }
 static void collect_stage_ms(DevCtx* c);
 
@@ -420,8 +427,10 @@ static int host_pipeline(DevCtx* c, const zkv_vk* vk, size_t m, size_t in_bytes,
         for (int k = h + 1; k < chunks; k += H) { size_t first = per * (size_t)k; pack(first, std::min(per, m - first), c->h_pin + offs[k]); ready[k].store(1, std::memory_order_release); }
     });
     pack(0, std::min(per, m), c->h_pin); ready[0].store(1);
-    std::vector<cudaEvent_t> evs;                    // piped: upload-done and chain-done events per piece
-    if (piped) { evs.resize(2 * (size_t)chunks, nullptr); for (auto& e : evs) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "cudaEventCreate"); }
+    std::vector<cudaEvent_t> evs;                    // piped: upload-done and chain-done events per piece; chunked: front-done event per chunk
+    const bool split = !piped && chunks > 1 && chunks <= DevCtx::NAUX;     // chunked: every chunk's front kernels first, side by side, then the heavy kernels
+    if (piped || split) { evs.resize((piped ? 2 : 1) * (size_t)chunks, nullptr); for (auto& e : evs) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "cudaEventCreate"); }
+    std::vector<Job> jobs(chunks);
     int used = 0;
     for (int k = 0; k < chunks && !rc; k++) {
         const size_t first = per * (size_t)k, cnt = std::min(per, m - first), in_off = offs[k];
@@ -432,9 +441,26 @@ static int host_pipeline(DevCtx* c, const zkv_vk* vk, size_t m, size_t in_bytes,
         while (!ready[k].load(std::memory_order_acquire)) std::this_thread::yield();
         rc = cudaMemcpyAsync(c->d_in + in_off, c->h_pin + in_off, bytes[k], cudaMemcpyHostToDevice, s_in) == cudaSuccess ? 0 : fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (host to device)");
         if (!rc && piped && (cudaEventRecord(evs[2 * k], s_in) != cudaSuccess || cudaStreamWaitEvent(s, evs[2 * k], 0) != cudaSuccess)) rc = fail(ZKV_ERR_CUDA, "event (upload done)");
-        if (!rc) { Job j = job(first, cnt, c->d_in + in_off); rc = enqueue_chain(c, j, 0, first, (int)cnt, s, chunks == 1, piped); }
+        if (rc) break;
+        jobs[k] = job(first, cnt, c->d_in + in_off);
+        if (split && !(jobs[k].all_fail || !vk->valid)) {
+            // interleaved with the heavy kernels of other chunks the front kernels (vk_x, the G2 check) run at a fraction of their occupancy and
+            // take block slots from them: all chunks run their front kernels first, concurrently with each other, then the heavy ones
+            rc = enqueue_chain(c, jobs[k], 0, first, (int)cnt, s, false, false, 1);
+            if (!rc && cudaEventRecord(evs[k], s) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "event (front done)");
+            continue;
+        }
+        rc = enqueue_chain(c, jobs[k], 0, first, (int)cnt, s, chunks == 1, piped);
         if (!rc && piped && (cudaEventRecord(evs[2 * k + 1], s) != cudaSuccess || cudaStreamWaitEvent(s_out, evs[2 * k + 1], 0) != cudaSuccess)) rc = fail(ZKV_ERR_CUDA, "event (chain done)");
         if (!rc && cudaMemcpyAsync(c->h_out + first, c->d_out + first, cnt, cudaMemcpyDeviceToHost, s_out) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (device to host)");
+    }
+    for (int k = 0; split && k < chunks && !rc; k++) {
+        if (jobs[k].all_fail || !vk->valid) continue;        // (that chunk ran its whole chain above)
+        const size_t first = per * (size_t)k, cnt = std::min(per, m - first);
+        cudaStream_t s = c->aux[k % DevCtx::NAUX];
+        for (int o = 0; o < chunks && !rc; o++) if (o != k && !(jobs[o].all_fail || !vk->valid) && cudaStreamWaitEvent(s, evs[o], 0) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "event wait (front done)");
+        if (!rc) rc = enqueue_chain(c, jobs[k], 0, first, (int)cnt, s, false, false, 2);
+        if (!rc && cudaMemcpyAsync(c->h_out + first, c->d_out + first, cnt, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (device to host)");
     }
     for (auto& t : helpers) t.join();
     if (rc) { cudaDeviceSynchronize(); for (auto e : evs) if (e) cudaEventDestroy(e); return rc; }
