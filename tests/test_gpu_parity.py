@@ -625,3 +625,25 @@ def test_one_handle_across_all_devices_matches_one_device(Z, gpu, fx):
         want = np.asarray(oracle(idx))
         assert (m[idx] == want).all(), shape
         assert 0 < int((m == 0).sum()) < n and len(set(m.tolist())) >= 3
+
+
+def test_campaign_batches_match_committed_oracle_digests(Z, gpu, consts):
+    """Two batches of the round-2 exactness campaign (2^16 mixed proofs each, one per proof shape) rebuilt from their seeds and verified
+    through the C ABI: the status bytes must hash to what the CPU oracle produced for the same batch (profiles/r2_campaign_oracle_digests.json,
+    written by tools/campaign_oracle.py from 10 092 544 oracle-verified proofs); the input fingerprints must agree as well."""
+    import hashlib, json, os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import campaign_common as CC
+    dg = {b["k"]: b for b in json.load(open(os.path.join(root, "profiles", "r2_campaign_oracle_digests.json")))["batches"]}
+    h = bytes.fromhex; r = consts["risc0_fixture"]
+    vk0, vk1 = CC.keys(gpu)
+    v0 = Z.RiscZeroVerifier(Z.VerificationKey(0, vk0.alpha, vk0.beta, vk0.gamma, vk0.delta, vk0.ic)); v0.initialize(h(r["control_root"]), h(r["bn254_control_id"]))
+    v1 = Z.Sp1Verifier(Z.VerificationKey(1, vk1.alpha, vk1.beta, vk1.gamma, vk1.delta, vk1.ic))
+    for k in (0, 1):
+        shape, b, fpr = CC.batch(gpu, k, vk0, vk1, v0.get_selector(), consts, CC.BATCH)
+        st = v0.verify_batch(b.seals, b.image_ids, b.journals) if shape == "risc0" else v1.verify_batch(b.vkeys, b.public_values, b.proofs)
+        st = np.asarray(st, dtype=np.uint8)
+        assert fpr == dg[k]["fingerprint"] and shape == dg[k]["shape"]
+        assert int((st == 0).sum()) == dg[k]["accepted"]
+        assert hashlib.sha256(st.tobytes()).hexdigest() == dg[k]["status_sha256"], k

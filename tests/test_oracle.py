@@ -212,3 +212,24 @@ def test_python_referee_agrees_on_every_mutation_class(fx):
     for shape in ("risc0", "sp1"):
         for c in want_classes:
             assert seen.get((shape, c), 0) >= 3, (shape, c, seen)
+
+
+def test_committed_campaign_digests_are_consistent():
+    """profiles/r2_campaign_oracle_digests.json (the CPU-oracle half of the >= 10^7-proof exactness campaign): 154 batches of 2^16 proofs, both
+    shapes, every mutation class present, only `valid` proofs accepted, histogram and class counts add up."""
+    import json, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = json.load(open(os.path.join(root, "profiles", "r2_campaign_oracle_digests.json")))
+    assert len(d["batches"]) == 154 and d["batch"] == 1 << 16 and d["classes"][0] == "valid"
+    tot = acc = 0
+    per = [0] * len(d["classes"])
+    for b in d["batches"]:
+        assert b["shape"] == ("risc0" if b["k"] % 2 == 0 else "sp1") and len(b["status_sha256"]) == 64
+        n = sum(c[0] for c in b["per_class"])
+        assert n == d["batch"] == sum(b["status_histogram"].values())
+        assert b["accepted"] == b["per_class"][0][1] == b["per_class"][0][0] == b["status_histogram"]["0"]      # every valid proof and nothing else
+        assert all(c[1] == 0 for c in b["per_class"][1:])
+        tot += n; acc += b["accepted"]
+        for i, c in enumerate(b["per_class"]):
+            per[i] += c[0]
+    assert tot == 10092544 >= 10 ** 7 and all(p > 400000 for p in per) and 0.45 < acc / tot < 0.55

@@ -52,7 +52,8 @@ CLASS_ID = {c: i for i, c in enumerate(CLASSES)}
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["compute", "compare"])
+    ap.add_argument("mode", choices=["compute", "compare", "digest", "check"])
+    ap.add_argument("--digests", default="profiles/r2_campaign_oracle_digests.json")
     ap.add_argument("--first", type=int, default=0); ap.add_argument("--count", type=int, default=160); ap.add_argument("--n", type=int, default=CC.BATCH)
     ap.add_argument("--out", default="gpurun_out/campaign_oracle"); ap.add_argument("--procs", type=int, default=4)
     ap.add_argument("--gpu", default="gpurun_out/campaign"); ap.add_argument("--oracle", default="gpurun_out/campaign_oracle"); ap.add_argument("--json", default="profiles/r2_campaign_oracle.json")
@@ -65,7 +66,42 @@ def main():
             for k, dt in pool.imap_unordered(compute_one, [(k, a.out, a.n) for k in range(a.first, a.first + a.count)]):
                 print("oracle batch %d done in %.0f s" % (k, dt), flush=True)
         return
+    import hashlib
     import numpy as np
+    if a.mode == "digest":
+        # the oracle's status bytes are 64 KiB per batch (10 MB for the campaign): what is committed is their SHA-256 per batch, with the input
+        # fingerprint, the accept count and the per-class accept / reject counts, so that the GPU half can be re-checked after any rebuild
+        # (mode `check`) without repeating the 2.5 CPU-hours of the oracle half
+        out = {"base_seed": CC.BASE_SEED, "batch": a.n, "classes": list(CLASSES), "batches": []}
+        k = 0
+        while os.path.exists(os.path.join(a.oracle, "oracle_%04d.json" % k)):
+            oj = json.load(open(os.path.join(a.oracle, "oracle_%04d.json" % k)))
+            o = np.fromfile(os.path.join(a.oracle, "oracle_%04d.bin" % k), dtype=np.uint8)
+            c = np.fromfile(os.path.join(a.oracle, "classes_%04d.bin" % k), dtype=np.uint8)
+            out["batches"].append({"k": k, "shape": oj["shape"], "fingerprint": oj["fingerprint"], "status_sha256": hashlib.sha256(o.tobytes()).hexdigest(),
+                                   "accepted": int((o == 0).sum()), "per_class": [[int((c == i).sum()), int(((c == i) & (o == 0)).sum())] for i in range(len(CLASSES))],
+                                   "status_histogram": {str(int(x)): int(n) for x, n in zip(*np.unique(o, return_counts=True))}})
+            k += 1
+        json.dump(out, open(a.digests, "w"))
+        print("wrote %s: %d batches, %d proofs" % (a.digests, k, k * a.n))
+        return
+    if a.mode == "check":
+        dg = json.load(open(a.digests)); man = json.load(open(os.path.join(a.gpu, "manifest.json")))
+        byk = {b["k"]: b for b in dg["batches"]}
+        tot = {"proofs": 0, "batches": 0, "batches_equal_to_oracle": 0, "fingerprint_mismatches": 0, "accepted": 0, "library": man.get("library")}
+        for e in man["batches"]:
+            b = byk.get(e["k"])
+            if b is None:
+                continue
+            g = np.fromfile(os.path.join(a.gpu, "status_%04d.bin" % e["k"]), dtype=np.uint8)
+            tot["batches"] += 1; tot["proofs"] += len(g); tot["accepted"] += int((g == 0).sum())
+            tot["fingerprint_mismatches"] += int(b["fingerprint"] != e["fingerprint"])
+            tot["batches_equal_to_oracle"] += int(hashlib.sha256(g.tobytes()).hexdigest() == b["status_sha256"] and b["fingerprint"] == e["fingerprint"])
+        tot["mismatching_batches"] = tot["batches"] - tot["batches_equal_to_oracle"]
+        tot["how"] = "SHA-256 of each batch's GPU status bytes against the committed digest of the oracle's status bytes for the same seeded batch (%s)" % a.digests
+        json.dump(tot, open(a.json, "w"), indent=1)
+        print(json.dumps(tot))
+        return
     man = json.load(open(os.path.join(a.gpu, "manifest.json")))
     tot = {"proofs": 0, "compared_1_to_1_with_oracle": 0, "mismatches": 0, "accepted": 0, "batches": 0, "fingerprint_mismatches": 0,
            "per_class": {c: {"proofs": 0, "accepted": 0, "mismatches": 0} for c in CLASSES}, "per_shape": collections.Counter(), "status_histogram": collections.Counter()}

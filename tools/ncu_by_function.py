@@ -17,10 +17,11 @@ def main(src, elf, kernel):
     hdr = rows[h]; ix = {k: i for i, k in enumerate(hdr)}
     stalls = [k for k in hdr if k.startswith("stall_") and "Not Issued" not in k]
     num = lambda x: int(float(x)) if x not in ("", "-") else 0
-    base = None
+    base = None; seen = set()
     by = collections.defaultdict(collections.Counter); tot = collections.Counter()
     for r in rows[h + 1:]:
-        if len(r) < len(hdr) or r[0] in ("Address", "Kernel Name"): continue
+        if len(r) < len(hdr) or r[0] in ("Address", "Kernel Name") or r[0] in seen: continue
+        seen.add(r[0])
         a = int(r[0], 16) if r[0].startswith("0x") else int(r[0])
         if base is None: base = a
         off = a - base
