@@ -353,6 +353,8 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
 // G2 check) run at a fraction of their own occupancy between the heavy blocks.  Automatic (setting 0): half-wave chunks below two waves,
 // one chain above.  A positive setting forces that many chunks.
 static size_t wave_proofs_of(const DevCtx* c) { return (size_t)c->sms * 2 * ZKV_HTPB; }
+// a partial last wave worth running as a chain of its own beside the whole waves: not so small that it does not matter, not so full that there is little to fill
+static bool worth_splitting(size_t rem, size_t wave) { return rem >= wave / 8 && rem <= wave * 5 / 8; }
 static int chunk_count(const DevCtx* c, size_t n, int setting) {
     if (n < (size_t)8192) return 1;
     if (setting >= 1) return setting;
@@ -384,6 +386,21 @@ static int run_verify(DevCtx* c, const Job& j) {
     if (c->busy && (j.n > c->cap || j.n > c->fes_cap || j.n * (size_t)ns * 8 > c->scal_words)) { CK(cudaEventSynchronize(c->ev_busy)); c->busy = false; }   // growing frees buffers an earlier asynchronous call may still use
     rc = ctx_reserve(c, j.n, (size_t)ns * 8); if (rc) return rc;
     int chunks = chunk_count(c, j.n, j.vk->tune.overlap_chunks.load());
+    {   // from two waves on (automatic setting): the whole waves as ONE chain of one-launch kernels, the partial last wave as a second chain
+        // beside it, whose blocks fill the slots the first chain's kernels leave at their ends (2^17 proofs = 3.46 waves: 64.4 against 68.9 ms)
+        const size_t wave = wave_proofs_of(c), whole = j.n / wave * wave, rem = j.n - whole;
+        if (chunks == 1 && j.vk->tune.overlap_chunks.load() == 0 && j.n >= 2 * wave && worth_splitting(rem, wave) && !(j.all_fail || !j.vk->valid)) {
+            rc = enqueue_chain(c, j, 0, 0, (int)j.n, c->stream, false, false, 1); if (rc) return rc;
+            CK(cudaEventRecord(c->ev_fork, c->stream));
+            const size_t off[2] = {0, whole}, len[2] = {whole, rem};
+            for (int k = 0; k < 2; k++) {
+                CK(cudaStreamWaitEvent(c->aux[k], c->ev_fork, 0));
+                rc = enqueue_chain(c, j, off[k], off[k], (int)len[k], c->aux[k], false, true, 2); if (rc) return rc;
+                CK(cudaEventRecord(c->ev_join[k], c->aux[k])); CK(cudaStreamWaitEvent(c->stream, c->ev_join[k], 0));
+            }
+            return 0;
+        }
+    }
     if (chunks <= 1) return enqueue_chain(c, j, 0, 0, (int)j.n, c->stream, true);
     if (j.all_fail || !j.vk->valid) return enqueue_chain(c, j, 0, 0, (int)j.n, c->stream, false);
     // the front kernels run once over the whole batch (at their own full occupancy), only the heavy kernels are chunked over the side streams
@@ -391,6 +408,17 @@ static int run_verify(DevCtx* c, const Job& j) {
     return fork_join(c, c->stream, j.n, chunks, [&](size_t o, int m, cudaStream_t s) { return enqueue_chain(c, j, o, o, m, s, false, false, 2); });
 }
 static void collect_stage_ms(DevCtx* c);
+// memcpy of a large block by up to four threads (one thread moves 5 - 10 GB/s into pinned memory: a 45 MB piece would cost as much as a wave of kernels)
+static void pcopy(void* dst, const void* src, size_t n) {
+    const size_t MIN = (size_t)2 << 20;
+    int parts = (int)std::min<size_t>(4, n / MIN);
+    if (parts <= 1) { memcpy(dst, src, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = (n / parts + 63) / 64 * 64;
+    for (int t = 1; t < parts; t++) { size_t o = per * t, l = std::min(per, n - o); th.emplace_back([=]() { memcpy((uint8_t*)dst + o, (const uint8_t*)src + o, l); }); }
+    memcpy(dst, src, per);
+    for (auto& t : th) t.join();
+}
 
 // Host-buffer form of a batch on one device, pipelined: the batch is cut like run_verify cuts it, and every chunk gets its own
 // pack (into its slice of the pinned staging buffer) -> H2D -> kernel chain -> D2H on a side stream, so packing and copying chunk k+1
@@ -401,72 +429,84 @@ template <class Pack, class MakeJob>
 static int host_pipeline(DevCtx* c, const zkv_vk* vk, size_t m, size_t in_bytes, int ns, Pack pack, MakeJob job) {
     if (c->busy) { CK(cudaEventSynchronize(c->ev_busy)); c->busy = false; }      // a host call blocks anyway: wait out an earlier asynchronous device call here
     int rc = ctx_reserve(c, m, (size_t)ns * 8); if (rc) return rc;
+    // Pieces of the batch, in upload order.  Below two waves (or with a forced chunk count): `chunks` equal pieces, each with its own side
+    // stream; every piece runs its front kernels first, side by side with the others', then the heavy ones (interleaved with heavy blocks,
+    // vk_x and the G2 check run at a fraction of their occupancy and take block slots from them).  From two waves on (automatic setting): the
+    // KERNELS of all whole waves run back to back on the main stream as one-launch kernels, in pieces of up to four waves whose packing, upload
+    // (side stream 0) and status download (side stream 1) overlap the kernels of the pieces around them; the partial last wave is a piece of
+    // its own, uploaded first, whose chain runs beside the main one (side stream 2) and fills the block slots its kernels leave at their ends.
+    struct Piece { size_t first, cnt; int lane; };      // lane 0: side stream per piece, 1: main stream (piped), 2: the remainder's stream (piped)
+    std::vector<Piece> pcs;
+    const size_t wave = wave_proofs_of(c);
     int chunks = chunk_count(c, m, vk->tune.overlap_chunks.load());
-    size_t per = (m + chunks - 1) / chunks;
-    per = (per + ZKV_HTPB - 1) / ZKV_HTPB * ZKV_HTPB;
-    // Large batches (automatic setting, one kernel chain): the KERNELS of the whole batch run back to back on the main stream, but the batch is
-    // still cut, at whole waves, into pieces whose packing, upload (side stream 0) and status download (side stream 1) overlap the kernels
-    // of the pieces before / after them: copy pipelining without co-scheduling kernels of different stages.
-    const bool piped = chunks == 1 && vk->tune.overlap_chunks.load() == 0 && m >= 2 * wave_proofs_of(c);
-    if (piped) per = wave_proofs_of(c) * std::min<size_t>(4, std::max<size_t>(1, m / wave_proofs_of(c) / 3));
-    chunks = (int)((m + per - 1) / per);
-    // pack(first, cnt, nullptr) returns the size of a chunk's block, so every chunk's region of the pinned staging buffer is known up front
-    // and the chunks can be packed by concurrent host threads: chunk 0 on this thread, the others on helpers.  Packing is a handful of bulk
-    // memcpy per chunk, i.e. memory-bandwidth work.
-    std::vector<size_t> bytes(chunks, 0), offs(chunks + 1, 0);
-    for (int k = 0; k < chunks; k++) { size_t first = per * (size_t)k; bytes[k] = pack(first, std::min(per, m - first), nullptr); offs[k + 1] = offs[k] + (bytes[k] + 255) / 256 * 256; }
+    const bool piped = chunks == 1 && vk->tune.overlap_chunks.load() == 0 && m >= 2 * wave;
+    if (piped) {
+        size_t whole = m / wave * wave, rem = m - whole;
+        if (!worth_splitting(rem, wave)) { whole = m; rem = 0; }
+        if (rem) pcs.push_back({whole, rem, 2});
+        const size_t ww = (whole + wave - 1) / wave, npieces = (ww + 3) / 4;            // main pieces of at most four waves, evened out
+        const size_t per = wave * ((ww + npieces - 1) / npieces);
+        for (size_t f = 0; f < whole; f += per) pcs.push_back({f, std::min(per, whole - f), 1});
+    } else {
+        size_t per = (m + chunks - 1) / chunks;
+        per = (per + ZKV_HTPB - 1) / ZKV_HTPB * ZKV_HTPB;
+        for (size_t f = 0; f < m; f += per) pcs.push_back({f, std::min(per, m - f), 0});
+    }
+    const int np = (int)pcs.size();
+    // pack(first, cnt, nullptr) returns the size of a piece's block, so every piece's region of the pinned staging buffer is known up front
+    // and the pieces can be packed by concurrent host threads: piece 0 on this thread, the others on up to 6 helpers (helper h packs pieces
+    // h + 1, h + 1 + H, ...); ready[k] flips when piece k's block is complete.  Packing is a handful of bulk memcpy per piece.
+    std::vector<size_t> bytes(np, 0), offs(np + 1, 0);
+    for (int k = 0; k < np; k++) { bytes[k] = pack(pcs[k].first, pcs[k].cnt, nullptr); offs[k + 1] = offs[k] + (bytes[k] + 255) / 256 * 256; }
     (void)in_bytes;
-    rc = ctx_stage(c, offs[chunks], m); if (rc) return rc;
-    // chunk 0 is packed here, the others by up to 6 helper threads (helper h packs chunks h + 1, h + 1 + H, ...); ready[k] flips when chunk k's
-    // block is complete, and the enqueue loop below waits for it right before the chunk's upload
-    const int H = std::min(chunks - 1, 6);
-    std::vector<std::atomic<int>> ready(chunks);
+    rc = ctx_stage(c, offs[np], m); if (rc) return rc;
+    const int H = std::min(np - 1, 6);
+    std::vector<std::atomic<int>> ready(np);
     for (auto& r : ready) r.store(0);
     std::vector<std::thread> helpers;
     for (int h = 0; h < H; h++) helpers.emplace_back([&, h]() {
-        for (int k = h + 1; k < chunks; k += H) { size_t first = per * (size_t)k; pack(first, std::min(per, m - first), c->h_pin + offs[k]); ready[k].store(1, std::memory_order_release); }
+        for (int k = h + 1; k < np; k += H) { pack(pcs[k].first, pcs[k].cnt, c->h_pin + offs[k]); ready[k].store(1, std::memory_order_release); }
     });
-    pack(0, std::min(per, m), c->h_pin); ready[0].store(1);
-    std::vector<cudaEvent_t> evs;                    // piped: upload-done and chain-done events per piece; chunked: front-done event per chunk
-    const bool split = !piped && chunks > 1 && chunks <= DevCtx::NAUX;     // chunked: every chunk's front kernels first, side by side, then the heavy kernels
-    if (piped || split) { evs.resize((piped ? 2 : 1) * (size_t)chunks, nullptr); for (auto& e : evs) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "cudaEventCreate"); }
-    std::vector<Job> jobs(chunks);
-    int used = 0;
-    for (int k = 0; k < chunks && !rc; k++) {
-        const size_t first = per * (size_t)k, cnt = std::min(per, m - first), in_off = offs[k];
-        cudaStream_t s = chunks == 1 ? c->stream : c->aux[k % DevCtx::NAUX];
-        cudaStream_t s_in = piped ? c->aux[0] : s, s_out = piped ? c->aux[1] : s;
-        if (piped) { s = c->stream; used = 2; }
-        else if (chunks > 1) used = std::max(used, k % DevCtx::NAUX + 1);
+    pack(pcs[0].first, pcs[0].cnt, c->h_pin); ready[0].store(1);
+    // two pieces of a large batch (up to four whole waves + the partial one) are scheduled like chunks: own streams, fronts first, then the
+    // heavy kernels (one launch each) side by side, exactly as run_verify schedules the device-resident form of the same batch
+    const bool pair = piped && np == 2;
+    if (pair) { pcs[0].lane = pcs[1].lane = 0; }
+    const bool split = (!piped && np > 1 && np <= DevCtx::NAUX) || pair;
+    const bool pipe_copies = piped && !pair;
+    std::vector<cudaEvent_t> evs;                    // piped: upload-done and chain-done events per piece; split: front-done event per piece
+    if (pipe_copies || split) { evs.resize((pipe_copies ? 2 : 1) * (size_t)np, nullptr); for (auto& e : evs) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "cudaEventCreate"); }
+    std::vector<Job> jobs(np);
+    auto kstream = [&](int k) { return pcs[k].lane == 1 ? c->stream : pcs[k].lane == 2 ? c->aux[2] : np == 1 ? c->stream : c->aux[k % DevCtx::NAUX]; };
+    for (int k = 0; k < np && !rc; k++) {
+        const size_t first = pcs[k].first, cnt = pcs[k].cnt, in_off = offs[k];
+        cudaStream_t s = kstream(k), s_in = pipe_copies ? c->aux[0] : s, s_out = pipe_copies ? c->aux[1] : s;
         while (!ready[k].load(std::memory_order_acquire)) std::this_thread::yield();
         rc = cudaMemcpyAsync(c->d_in + in_off, c->h_pin + in_off, bytes[k], cudaMemcpyHostToDevice, s_in) == cudaSuccess ? 0 : fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (host to device)");
-        if (!rc && piped && (cudaEventRecord(evs[2 * k], s_in) != cudaSuccess || cudaStreamWaitEvent(s, evs[2 * k], 0) != cudaSuccess)) rc = fail(ZKV_ERR_CUDA, "event (upload done)");
+        if (!rc && pipe_copies && (cudaEventRecord(evs[2 * k], s_in) != cudaSuccess || cudaStreamWaitEvent(s, evs[2 * k], 0) != cudaSuccess)) rc = fail(ZKV_ERR_CUDA, "event (upload done)");
         if (rc) break;
         jobs[k] = job(first, cnt, c->d_in + in_off);
         if (split && !(jobs[k].all_fail || !vk->valid)) {
-            // interleaved with the heavy kernels of other chunks the front kernels (vk_x, the G2 check) run at a fraction of their occupancy and
-            // take block slots from them: all chunks run their front kernels first, concurrently with each other, then the heavy ones
             rc = enqueue_chain(c, jobs[k], 0, first, (int)cnt, s, false, false, 1);
             if (!rc && cudaEventRecord(evs[k], s) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "event (front done)");
             continue;
         }
-        rc = enqueue_chain(c, jobs[k], 0, first, (int)cnt, s, chunks == 1, piped);
-        if (!rc && piped && (cudaEventRecord(evs[2 * k + 1], s) != cudaSuccess || cudaStreamWaitEvent(s_out, evs[2 * k + 1], 0) != cudaSuccess)) rc = fail(ZKV_ERR_CUDA, "event (chain done)");
+        rc = enqueue_chain(c, jobs[k], 0, first, (int)cnt, s, np == 1, piped);
+        if (!rc && pipe_copies && (cudaEventRecord(evs[2 * k + 1], s) != cudaSuccess || cudaStreamWaitEvent(s_out, evs[2 * k + 1], 0) != cudaSuccess)) rc = fail(ZKV_ERR_CUDA, "event (chain done)");
         if (!rc && cudaMemcpyAsync(c->h_out + first, c->d_out + first, cnt, cudaMemcpyDeviceToHost, s_out) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (device to host)");
     }
-    for (int k = 0; split && k < chunks && !rc; k++) {
-        if (jobs[k].all_fail || !vk->valid) continue;        // (that chunk ran its whole chain above)
-        const size_t first = per * (size_t)k, cnt = std::min(per, m - first);
-        cudaStream_t s = c->aux[k % DevCtx::NAUX];
-        for (int o = 0; o < chunks && !rc; o++) if (o != k && !(jobs[o].all_fail || !vk->valid) && cudaStreamWaitEvent(s, evs[o], 0) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "event wait (front done)");
-        if (!rc) rc = enqueue_chain(c, jobs[k], 0, first, (int)cnt, s, false, false, 2);
-        if (!rc && cudaMemcpyAsync(c->h_out + first, c->d_out + first, cnt, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (device to host)");
+    for (int k = 0; split && k < np && !rc; k++) {
+        if (jobs[k].all_fail || !vk->valid) continue;        // (that piece ran its whole chain above)
+        cudaStream_t s = kstream(k);
+        for (int o = 0; o < np && !rc; o++) if (o != k && !(jobs[o].all_fail || !vk->valid) && cudaStreamWaitEvent(s, evs[o], 0) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "event wait (front done)");
+        if (!rc) rc = enqueue_chain(c, jobs[k], 0, pcs[k].first, (int)pcs[k].cnt, s, false, pair, 2);
+        if (!rc && cudaMemcpyAsync(c->h_out + pcs[k].first, c->d_out + pcs[k].first, pcs[k].cnt, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (device to host)");
     }
     for (auto& t : helpers) t.join();
     if (rc) { cudaDeviceSynchronize(); for (auto e : evs) if (e) cudaEventDestroy(e); return rc; }
-    if (chunks == 1) { CK(cudaStreamSynchronize(c->stream)); collect_stage_ms(c); }
+    if (np == 1) { CK(cudaStreamSynchronize(c->stream)); collect_stage_ms(c); }
     else {
-        for (int a = 0; a < used; a++) CK(cudaStreamSynchronize(c->aux[a]));
+        for (int a = 0; a < DevCtx::NAUX; a++) CK(cudaStreamSynchronize(c->aux[a]));
         if (piped) CK(cudaStreamSynchronize(c->stream));
     }
     for (auto e : evs) if (e) cudaEventDestroy(e);
@@ -513,7 +553,7 @@ extern "C" int zkv_groth16_verify_batch(const zkv_vk* vk, const uint8_t* proofs,
             size_t m = std::min(MAX_CHUNK, e - s0);
             int rc = host_pipeline(c, vk, m, m * (256 + (size_t)k * 32), k,
                 [&](size_t first, size_t cnt, uint8_t* dst) -> size_t {
-                    if (dst) { memcpy(dst, proofs + (s0 + first) * 256, cnt * 256); memcpy(dst + cnt * 256, signals + (s0 + first) * (size_t)k * 32, cnt * (size_t)k * 32); }
+                    if (dst) { pcopy(dst, proofs + (s0 + first) * 256, cnt * 256); pcopy(dst + cnt * 256, signals + (s0 + first) * (size_t)k * 32, cnt * (size_t)k * 32); }
                     return cnt * (256 + (size_t)k * 32);
                 },
                 [&](size_t first, size_t cnt, uint8_t* d) -> Job {
@@ -640,7 +680,7 @@ static int risc0_batch(const zkv_risc0* h, const uint8_t* seals, const uint64_t*
                     memcpy(p, seal_off + i0, (cnt + 1) * 8); p += (cnt + 1) * 8;
                     memcpy(p, a32 + i0 * 32, cnt * 32); p += cnt * 32;
                     if (!integrity) { memcpy(p, b32 + i0 * 32, cnt * 32); p += cnt * 32; }
-                    memcpy(p, seals + seal_off[i0], bytes); p += bytes;
+                    pcopy(p, seals + seal_off[i0], bytes); p += bytes;
                     return (size_t)(p - dst) + 320;
                 },
                 [&](size_t first, size_t cnt, uint8_t* d) -> Job {
@@ -723,8 +763,8 @@ extern "C" int zkv_sp1_verify_batch(const zkv_sp1* h, const uint8_t* vkeys, cons
                     memcpy(p, proof_off + i0, (cnt + 1) * 8); p += (cnt + 1) * 8;
                     memcpy(p, pv_off + i0, (cnt + 1) * 8); p += (cnt + 1) * 8;
                     memcpy(p, vkeys + i0 * 32, cnt * 32); p += cnt * 32;
-                    memcpy(p, proofs + proof_off[i0], pr); p += pr;
-                    memcpy(p, public_values + pv_off[i0], pv); p += pv;
+                    pcopy(p, proofs + proof_off[i0], pr); p += pr;
+                    pcopy(p, public_values + pv_off[i0], pv); p += pv;
                     return (size_t)(p - dst) + 320;
                 },
                 [&](size_t first, size_t cnt, uint8_t* d) -> Job {
