@@ -647,3 +647,44 @@ def test_campaign_batches_match_committed_oracle_digests(Z, gpu, consts):
         assert fpr == dg[k]["fingerprint"] and shape == dg[k]["shape"]
         assert int((st == 0).sum()) == dg[k]["accepted"]
         assert hashlib.sha256(st.tobytes()).hexdigest() == dg[k]["status_sha256"], k
+
+
+def test_large_batch_schedules_agree(Z, gpu, fx):
+    """Batches of two waves and more take other schedules than the four half-wave chunks of 2^16 proofs (csrc/zkv.cu chunk_count, run_verify,
+    host_pipeline): whole waves as one chain + the partial last wave beside it, and for host buffers pieces of up to four waves with pipelined
+    copies.  A mixed 6.4-wave batch through (a) the host-buffer call, (b) the device-resident call, (c) a forced 4-chunk host call and (d) a
+    forced single chain must give the same status bytes, equal to the generator's expectation everywhere and to the oracle on a sample; a
+    2.5-wave batch (two pieces scheduled like chunks) as well."""
+    import torch
+    from stylus_zkvm_verifiers_b200 import synth as S
+    wave = Z.wave_proofs(0, 0)
+    vk = S.make_vk(gpu, 0, 6, 0xB2000001)
+    kv = Z.VerificationKey(0, vk.alpha, vk.beta, vk.gamma, vk.delta, vk.ic)
+    v = Z.RiscZeroVerifier(kv); v.initialize(fx["control_root"], fx["bn254_control_id"])
+    ro = O.Risc0Oracle(oracle_vk(vk)); ro.initialize(fx["control_root"], fx["bn254_control_id"])
+    for n, seed in ((6 * wave + (2 * wave) // 5 + 37, 0xB2000041), (2 * wave + wave // 2 + 5, 0xB2000043)):
+        b = S.make_risc0_batch(gpu, vk, v.get_selector(), fx["control_root"], fx["bn254_control_id"], fx["sys0"], n, seed, pool=512)
+        S.mutate_risc0(b, gpu, S.SplitMix64(seed + 1))
+        for i in range(n):                               # the device entry point takes fixed 260-byte records: keep malformed lengths out
+            if len(b.seals[i]) != 260:
+                b.seals[i] = (b.seals[i] + bytes(260))[:260]; b.expect[i] = None
+        assert v.tune("overlap") == 0
+        host = np.asarray(v.verify_batch(b.seals, b.image_ids, b.journals))
+        t = lambda blobs: torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8).cuda()
+        d_s, d_i, d_j = t(b.seals), t(b.image_ids), t(b.journals)
+        d_st = torch.full((n,), 255, dtype=torch.uint8, device="cuda")
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            v.verify_batch_device(0, d_s.data_ptr(), d_i.data_ptr(), d_j.data_ptr(), n, d_st.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        dev = d_st.cpu().numpy()
+        v.tune("overlap", 4); forced4 = np.asarray(v.verify_batch(b.seals, b.image_ids, b.journals))
+        v.tune("overlap", 1); serial = np.asarray(v.verify_batch(b.seals, b.image_ids, b.journals))
+        v.tune("overlap", 0)
+        assert (host == dev).all() and (host == forced4).all() and (host == serial).all(), n
+        bad = [i for i in range(n) if b.expect[i] is not None and host[i] != b.expect[i]]
+        assert not bad, bad[:10]
+        idx = list(range(64)) + list(range(n - 64, n)) + [wave * k + d for k in range(1, n // wave + 1) for d in (-1, 0, 1) if wave * k + d < n]
+        want = ro.verify_batch([b.seals[i] for i in idx], [b.image_ids[i] for i in idx], [b.journals[i] for i in idx])
+        assert host[idx].tolist() == np.asarray(want).tolist()
+        assert 0 < int((host == 0).sum()) < n and len(set(host.tolist())) >= 3
