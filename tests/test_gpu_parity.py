@@ -688,3 +688,48 @@ def test_large_batch_schedules_agree(Z, gpu, fx):
         want = ro.verify_batch([b.seals[i] for i in idx], [b.image_ids[i] for i in idx], [b.journals[i] for i in idx])
         assert host[idx].tolist() == np.asarray(want).tolist()
         assert 0 < int((host == 0).sum()) < n and len(set(host.tolist())) >= 3
+
+
+def test_async_device_calls_share_the_workspace_safely(Z, gpu, fx):
+    """the *_device entry points return before their kernels finish and share one workspace per key and device.  A device call
+    on stream X followed immediately by a host batch call on the same key, and two device calls on two different streams back to back, must
+    each produce their own correct status bytes (the library orders later users of the workspace behind a busy event); a NULL stream means the
+    legacy default stream, so work queued there before the call is ordered before it."""
+    import torch
+    from stylus_zkvm_verifiers_b200 import synth as S
+    vk = S.make_vk(gpu, 0, 6, 0xB2000051)
+    kv = Z.VerificationKey(0, vk.alpha, vk.beta, vk.gamma, vk.delta, vk.ic)
+    v = Z.RiscZeroVerifier(kv); v.initialize(fx["control_root"], fx["bn254_control_id"])
+    t = lambda blobs: torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8).cuda()
+
+    def mk(n, seed):
+        b = S.make_risc0_batch(gpu, vk, v.get_selector(), fx["control_root"], fx["bn254_control_id"], fx["sys0"], n, seed, pool=64)
+        S.mutate_risc0(b, gpu, S.SplitMix64(seed + 7))
+        keep = [i for i in range(n) if len(b.seals[i]) == 260]
+        return [b.seals[i] for i in keep], [b.image_ids[i] for i in keep], [b.journals[i] for i in keep]
+    A, B = mk(9000, 0xB2000052), mk(7000, 0xB2000053)          # > 8192 proofs: A is cut into chunks on side streams
+    wantA = np.asarray(v.verify_batch(*A)); wantB = np.asarray(v.verify_batch(*B))
+    assert 0 < int((wantA == 0).sum()) < len(wantA) and wantA[:len(wantB)].tolist() != wantB.tolist()
+    dA, dB = [t(x) for x in A], [t(x) for x in B]
+    for rep in range(3):
+        sx, sy = torch.cuda.Stream(), torch.cuda.Stream()
+        stA = torch.full((len(wantA),), 255, dtype=torch.uint8, device="cuda"); stB = torch.full((len(wantB),), 255, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        # device call on stream X, then at once a host call on the same key
+        v.verify_batch_device(0, dA[0].data_ptr(), dA[1].data_ptr(), dA[2].data_ptr(), len(wantA), stA.data_ptr(), sx.cuda_stream)
+        hostB = np.asarray(v.verify_batch(*B))
+        sx.synchronize()
+        assert hostB.tolist() == wantB.tolist() and stA.cpu().numpy().tolist() == wantA.tolist(), rep
+        # two device calls on two streams back to back
+        stA.fill_(255); stB.fill_(255); torch.cuda.synchronize()
+        v.verify_batch_device(0, dA[0].data_ptr(), dA[1].data_ptr(), dA[2].data_ptr(), len(wantA), stA.data_ptr(), sx.cuda_stream)
+        v.verify_batch_device(0, dB[0].data_ptr(), dB[1].data_ptr(), dB[2].data_ptr(), len(wantB), stB.data_ptr(), sy.cuda_stream)
+        torch.cuda.synchronize()
+        assert stA.cpu().numpy().tolist() == wantA.tolist() and stB.cpu().numpy().tolist() == wantB.tolist(), rep
+    # NULL stream = legacy default stream: the fill queued on it before the call must not overwrite the results
+    stB = torch.empty((len(wantB),), dtype=torch.uint8, device="cuda")
+    with torch.cuda.stream(torch.cuda.default_stream()):
+        stB.fill_(255)
+        v.verify_batch_device(0, dB[0].data_ptr(), dB[1].data_ptr(), dB[2].data_ptr(), len(wantB), stB.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert stB.cpu().numpy().tolist() == wantB.tolist()
