@@ -182,6 +182,51 @@ __global__ void k_vkx(int n, const uint32_t* scal, int ns, int nwin, const g1aff
 }
 
 // K2: order-r membership of B (EIP-197; the reference reaches it through ecPairing, groth16.rs:121-125)
+// g2_in_subgroup of bn254.cuh with the running point in REGISTERS and the Fp2 products through the by-value multiplier of lazy.cuh
+// (f2v_mul / f2v_sqr: operands and results in registers, one copy of the code): the pointer-passing form keeps every Fp2 value in a
+// 2.9 KB per-thread stack frame.  Same formulas in the same order (g2_dbl, g2_add_affine with its special cases), so the same accept set
+// and the same intermediate values; the tail ([u+1]Q + psi + psi^2 against psi^3 of [2u]Q) runs through the bn254.cuh routines.
+#if defined(__CUDACC__)
+__device__ __noinline__ bool g2v_in_subgroup(fp2 qx, fp2 qy) {
+    fp2 X = qx, Y = qy, Z = f2_one();
+    const fp2 ny = f2v_neg(qy);
+    for (int i = ZKV_U_NAF_LEN - 2; i >= 0; i--) {
+        {   // doubling (g2_dbl)
+            fp2 A = f2v_sqr(X), B = f2v_sqr(Y), C = f2v_sqr(B);
+            fp2 D = f2v_dbl(f2v_sub(f2v_sub(f2v_sqr(f2v_add(X, B)), A), C));
+            fp2 E = f2v_add(f2v_dbl(A), A), F = f2v_sqr(E);
+            fp2 X3 = f2v_sub(F, f2v_dbl(D));
+            fp2 Y3 = f2v_sub(f2v_mul(E, f2v_sub(D, X3)), f2v_dbl(f2v_dbl(f2v_dbl(C))));
+            Z = f2v_dbl(f2v_mul(Y, Z)); X = X3; Y = Y3;
+        }
+        const int d = C_U_NAF[i];
+        if (d) {    // mixed addition of +-Q (g2_add_affine)
+            const fp2 ay = d > 0 ? qy : ny;
+            if (f2_is_zero(Z)) { X = qx; Y = ay; Z = f2_one(); continue; }
+            fp2 z1z1 = f2v_sqr(Z), u2 = f2v_mul(qx, z1z1), s2 = f2v_mul(f2v_mul(ay, Z), z1z1);
+            fp2 h = f2v_sub(u2, X), rr = f2v_sub(s2, Y);
+            if (f2_is_zero(h)) {
+                if (f2_is_zero(rr)) { g2j p, r; p.x = X; p.y = Y; p.z = Z; g2_dbl(r, p); X = r.x; Y = r.y; Z = r.z; }
+                else { X = f2_one(); Y = f2_one(); Z = f2_zero(); }
+                continue;
+            }
+            fp2 hh = f2v_sqr(h), hhh = f2v_mul(hh, h), v = f2v_mul(X, hh);
+            fp2 X3 = f2v_sub(f2v_sub(f2v_sqr(rr), hhh), f2v_dbl(v));
+            fp2 Y3 = f2v_sub(f2v_mul(rr, f2v_sub(v, X3)), f2v_mul(Y, hhh));
+            Z = f2v_mul(Z, h); X = X3; Y = Y3;
+        }
+    }
+    g2j q, uq, lhs, t, p1, p2, p3;
+    q.x = qx; q.y = qy; q.z = f2_one(); uq.x = X; uq.y = Y; uq.z = Z;
+    g2_add(lhs, uq, q);
+    g2_psi(p1, uq, 1); g2_add(t, lhs, p1); lhs = t;
+    g2_psi(p2, uq, 2); g2_add(t, lhs, p2); lhs = t;
+    g2_dbl(t, uq); g2_psi(p3, t, 3);
+    return g2j_eq(lhs, p3);
+}
+#else
+static inline bool g2v_in_subgroup(fp2 qx, fp2 qy) { return g2_in_subgroup(qx, qy); }
+#endif
 __global__ void k_g2_check(int n, const fp2* bx, const fp2* by, uint8_t* flags) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -189,7 +234,13 @@ __global__ void k_g2_check(int n, const fp2* bx, const fp2* by, uint8_t* flags) 
     if (fl & F_REJECT) return;
     fp2 x = bx[i], y = by[i];
     if (f2_is_zero(x) && f2_is_zero(y)) return;      // infinity is a member
-    if (!g2_in_subgroup(x, y)) flags[i] = fl | F_INVALID;
+    if (!g2v_in_subgroup(x, y)) flags[i] = fl | F_INVALID;
+}
+
+// flags[i] |= extra[i] (vk_x's flag bits when it ran beside the G2 check on a scratch array)
+__global__ void k_or_flags(int n, uint8_t* flags, const uint8_t* extra) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && extra[i]) flags[i] |= extra[i];
 }
 
 // K6: multi-Miller loop.  Pair 0 = (px[0], variable G2); pairs 1..nfixed = (px[j], fixed G2 with line table tabs[j-1]).

@@ -64,7 +64,7 @@ struct DevCtx {
     size_t cap = 0;
     fp* px[4] = {nullptr, nullptr, nullptr, nullptr}; fp* py[4] = {nullptr, nullptr, nullptr, nullptr};   // four slices of ONE allocation each, `stride` entries apart (pair-major: the general Miller kernel indexes [j * stride + i])
     size_t stride = 0; uint8_t* pskip = nullptr;                                                          // pairing service: per-pair skip bytes, 4 x stride
-    fp2 *qx = nullptr, *qy = nullptr; fp12* f = nullptr; g2j* rst = nullptr; fp* sl = nullptr; fp12* fes = nullptr; size_t fes_cap = 0; uint8_t *flags = nullptr, *status = nullptr; uint32_t* scal = nullptr; size_t scal_words = 0;
+    fp2 *qx = nullptr, *qy = nullptr; fp12* f = nullptr; g2j* rst = nullptr; fp* sl = nullptr; fp12* fes = nullptr; size_t fes_cap = 0; uint8_t *flags = nullptr, *status = nullptr;      /* status: scratch flag bytes of vk_x when it runs beside the G2 check */ uint32_t* scal = nullptr; size_t scal_words = 0;
     // staging
     uint8_t* d_in = nullptr; size_t d_in_cap = 0; uint8_t* d_out = nullptr; size_t d_out_cap = 0;
     uint8_t* h_pin = nullptr; size_t h_pin_cap = 0; uint8_t* h_out = nullptr; size_t h_out_cap = 0;
@@ -292,12 +292,28 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
             CK(cudaGetLastError());
             return 0;
         }
-        k_vkx<<<nblk(m), TPB, 0, s>>>(m, scal, ns, nwin, tab, j.base, c->px[2] + o, c->py[2] + o, flags);
-        if (timed) CK(cudaEventRecord(c->ev[2], s));
-        DBG("decode / signals / vk_x");
-        k_g2_check<<<nblk(m), TPB, 0, s>>>(m, c->qx + o, c->qy + o, flags);
-        DBG("k_g2_check");
-        if (timed) CK(cudaEventRecord(c->ev[3], s));
+        // Front phase of a whole chunked batch (run_verify): vk_x and the G2 check are independent (the check reads what k_decode wrote, both
+        // touch disjoint flag bits of different proofs' bytes only through their own thread), and each is 1.7 waves of its own block shape at 2^16
+        // proofs: side by side on two streams they fill each other's partial waves.  F_SKIPX (vk_x = infinity) and F_INVALID (B outside the
+        // subgroup) live in the same flag byte of a proof, so the two kernels must not write it concurrently: vk_x gets a flag array of its own
+        // (the front-phase scratch) that is OR-ed in by the G2 check's stream afterwards.
+        const bool fork_front = phases == 1 && !timed && s == c->stream && m >= 8192;
+        if (fork_front) {
+            CK(cudaEventRecord(c->ev_fork, s)); CK(cudaStreamWaitEvent(c->aux[0], c->ev_fork, 0));
+            k_g2_check<<<nblk(m), TPB, 0, c->aux[0]>>>(m, c->qx + o, c->qy + o, flags);
+            CK(cudaMemsetAsync(c->status + o, 0, m, s));
+            k_vkx<<<nblk(m), TPB, 0, s>>>(m, scal, ns, nwin, tab, j.base, c->px[2] + o, c->py[2] + o, c->status + o);
+            CK(cudaEventRecord(c->ev_join[0], c->aux[0])); CK(cudaStreamWaitEvent(s, c->ev_join[0], 0));
+            k_or_flags<<<nblk(m, 256), 256, 0, s>>>(m, flags, c->status + o);
+            g_launches += 1;
+        } else {
+            k_vkx<<<nblk(m), TPB, 0, s>>>(m, scal, ns, nwin, tab, j.base, c->px[2] + o, c->py[2] + o, flags);
+            if (timed) CK(cudaEventRecord(c->ev[2], s));
+            DBG("decode / signals / vk_x");
+            k_g2_check<<<nblk(m), TPB, 0, s>>>(m, c->qx + o, c->qy + o, flags);
+            DBG("k_g2_check");
+            if (timed) CK(cudaEventRecord(c->ev[3], s));
+        }
         if (!(phases & 2)) { g_launches += 4; CK(cudaGetLastError()); return 0; }
     }
     MillerArgs a; memset(&a, 0, sizeof a);
