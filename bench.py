@@ -219,17 +219,18 @@ def main():
     if args.shape == "risc0":
         d_a, d_b, d_c = t8(batch.seals), t8(batch.image_ids), t8(batch.journals)
         launch = lambda st, stream, m=n: v.verify_batch_device(dev, d_a.data_ptr(), d_b.data_ptr(), d_c.data_ptr(), m, st.data_ptr(), stream)
-        h_blob = np.frombuffer(b"".join(batch.seals), dtype=np.uint8); h_off = np.arange(n + 1, dtype=np.uint64) * 260
-        h_b = np.frombuffer(b"".join(batch.image_ids), dtype=np.uint8); h_c = np.frombuffer(b"".join(batch.journals), dtype=np.uint8)
+        # e2e inputs live in page-locked host memory (the contract's "pinned host memory"): the library uploads such arrays in place
+        h_blob = Z.pinned_copy(np.frombuffer(b"".join(batch.seals), dtype=np.uint8)); h_off = Z.pinned_copy(np.arange(n + 1, dtype=np.uint64) * 260)
+        h_b = Z.pinned_copy(np.frombuffer(b"".join(batch.image_ids), dtype=np.uint8)); h_c = Z.pinned_copy(np.frombuffer(b"".join(batch.journals), dtype=np.uint8))
         e2e_call = lambda out: v.verify_batch_packed(h_blob, h_off, h_b, h_c, n, out)
         h2d = n * (256 + 64)
         W_M = W_RISC0_M
     else:
         d_a, d_b, d_c = t8(batch.proofs), t8(batch.vkeys), t8(batch.public_values)
         launch = lambda st, stream, m=n: v.verify_batch_device(dev, d_b.data_ptr(), d_c.data_ptr(), 96, d_a.data_ptr(), m, st.data_ptr(), stream)
-        h_blob = np.frombuffer(b"".join(batch.proofs), dtype=np.uint8); h_off = np.arange(n + 1, dtype=np.uint64) * 260
-        h_b = np.frombuffer(b"".join(batch.vkeys), dtype=np.uint8); h_c = np.frombuffer(b"".join(batch.public_values), dtype=np.uint8)
-        h_voff = np.arange(n + 1, dtype=np.uint64) * 96
+        h_blob = Z.pinned_copy(np.frombuffer(b"".join(batch.proofs), dtype=np.uint8)); h_off = Z.pinned_copy(np.arange(n + 1, dtype=np.uint64) * 260)
+        h_b = Z.pinned_copy(np.frombuffer(b"".join(batch.vkeys), dtype=np.uint8)); h_c = Z.pinned_copy(np.frombuffer(b"".join(batch.public_values), dtype=np.uint8))
+        h_voff = Z.pinned_copy(np.arange(n + 1, dtype=np.uint64) * 96)
         e2e_call = lambda out: v.verify_batch_packed(h_b, h_c, h_voff, h_blob, h_off, n, out)
         h2d = n * (256 + 32 + 96 + 8)
         W_M = W_SP1_M

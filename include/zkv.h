@@ -190,6 +190,12 @@ long long zkv_wave_proofs(int device, int kernel);
 /* integer-pipe microbenchmark (roofline denominator): returns measured IMAD.WIDE.U32 results/s and
  * Fp-multiplications/s on `device` */
 int zkv_imad_peak(int device, double* wide_per_s, double* fpmul_per_s);
+/* Page-locked host memory for the batch calls.  When EVERY input array of a zkv_risc0_verify[_integrity]_batch / zkv_sp1_verify_batch /
+ * zkv_groth16_verify_batch call lies in page-locked memory (these two functions, cudaHostAlloc or cudaHostRegister), the arrays are uploaded
+ * from where they are, one asynchronous copy per array slice; otherwise they are first gathered into the library's own pinned staging buffer
+ * by a few host threads (one extra pass over the input in host memory).  Results are identical. */
+void* zkv_host_alloc(size_t bytes);
+void zkv_host_free(void* p);
 /* Known-answer self test of the production kernels on `device`: the reference's two golden proofs (the RISC Zero seal and the SP1 proof
  * of examples/{risc0,sp1}-verifier/examples/interact.rs, with the embedded keys of risc0/crypto.rs:16-79 and sp1/crypto.rs:7-81) must be
  * accepted and a one-bit tamper of each rejected with VerificationFailed, in both kernel layouts.  0 = pass, ZKV_ERR_STATE = a kernel

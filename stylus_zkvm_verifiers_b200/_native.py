@@ -60,6 +60,8 @@ _SIGS = {
     "zkv_wave_proofs": (C.c_longlong, [C.c_int, C.c_int]),
     "zkv_imad_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "zkv_self_test": (C.c_int, [C.c_int]),
+    "zkv_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "zkv_host_free": (None, [C.c_void_p]),
 }
 EXPORTS = tuple(_SIGS)
 

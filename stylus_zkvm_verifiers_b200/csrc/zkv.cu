@@ -441,8 +441,25 @@ static void pcopy(void* dst, const void* src, size_t n) {
 // overlap the kernels of chunk k.  pack(first, count, dst) writes the chunk's input block and returns its size in bytes;
 // job(first, count, d_block) describes the chunk, with pointers into its device input block and d_status = c->d_out + first.
 // in_bytes: upper bound of the whole batch's input.  On return c->h_out[0..m) holds the status bytes.
+// Where a piece's input block is assembled: in the pinned staging buffer (memcpy; large segments by several threads), or - when every source
+// array of the call already lives in page-locked memory (cudaHostAlloc / cudaHostRegister) - straight in device memory, one asynchronous
+// upload per segment from the caller's own arrays, with no host copy at all.
+struct Sink {
+    uint8_t* host; uint8_t* dev; cudaStream_t s; int bad;
+    void put(size_t off, const void* src, size_t n, bool big = false) {
+        if (!n) return;
+        if (host) { if (big) pcopy(host + off, src, n); else memcpy(host + off, src, n); }
+        else if (cudaMemcpyAsync(dev + off, src, n, cudaMemcpyHostToDevice, s) != cudaSuccess) bad = 1;
+    }
+};
+static bool is_pinned(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
 template <class Pack, class MakeJob>
-static int host_pipeline(DevCtx* c, const zkv_vk* vk, size_t m, size_t in_bytes, int ns, Pack pack, MakeJob job) {
+static int host_pipeline(DevCtx* c, const zkv_vk* vk, size_t m, size_t in_bytes, int ns, Pack pack, MakeJob job, bool direct = false) {
     if (c->busy) { CK(cudaEventSynchronize(c->ev_busy)); c->busy = false; }      // a host call blocks anyway: wait out an earlier asynchronous device call here
     int rc = ctx_reserve(c, m, (size_t)ns * 8); if (rc) return rc;
     // Pieces of the batch, in upload order.  Below two waves (or with a forced chunk count): `chunks` equal pieces, each with its own side
@@ -473,17 +490,17 @@ static int host_pipeline(DevCtx* c, const zkv_vk* vk, size_t m, size_t in_bytes,
     // and the pieces can be packed by concurrent host threads: piece 0 on this thread, the others on up to 6 helpers (helper h packs pieces
     // h + 1, h + 1 + H, ...); ready[k] flips when piece k's block is complete.  Packing is a handful of bulk memcpy per piece.
     std::vector<size_t> bytes(np, 0), offs(np + 1, 0);
-    for (int k = 0; k < np; k++) { bytes[k] = pack(pcs[k].first, pcs[k].cnt, nullptr); offs[k + 1] = offs[k] + (bytes[k] + 255) / 256 * 256; }
+    for (int k = 0; k < np; k++) { bytes[k] = pack(pcs[k].first, pcs[k].cnt, (Sink*)nullptr); offs[k + 1] = offs[k] + (bytes[k] + 255) / 256 * 256; }
     (void)in_bytes;
     rc = ctx_stage(c, offs[np], m); if (rc) return rc;
-    const int H = std::min(np - 1, 6);
+    const int H = direct ? 0 : std::min(np - 1, 6);
     std::vector<std::atomic<int>> ready(np);
-    for (auto& r : ready) r.store(0);
+    for (auto& r : ready) r.store(direct ? 1 : 0);
     std::vector<std::thread> helpers;
     for (int h = 0; h < H; h++) helpers.emplace_back([&, h]() {
-        for (int k = h + 1; k < np; k += H) { pack(pcs[k].first, pcs[k].cnt, c->h_pin + offs[k]); ready[k].store(1, std::memory_order_release); }
+        for (int k = h + 1; k < np; k += H) { Sink sk{c->h_pin + offs[k], nullptr, nullptr, 0}; pack(pcs[k].first, pcs[k].cnt, &sk); ready[k].store(1, std::memory_order_release); }
     });
-    pack(pcs[0].first, pcs[0].cnt, c->h_pin); ready[0].store(1);
+    if (!direct) { Sink sk{c->h_pin, nullptr, nullptr, 0}; pack(pcs[0].first, pcs[0].cnt, &sk); ready[0].store(1); }
     // two pieces of a large batch (up to four whole waves + the partial one) are scheduled like chunks: own streams, fronts first, then the
     // heavy kernels (one launch each) side by side, exactly as run_verify schedules the device-resident form of the same batch
     const bool pair = piped && np == 2;
@@ -498,7 +515,8 @@ static int host_pipeline(DevCtx* c, const zkv_vk* vk, size_t m, size_t in_bytes,
         const size_t first = pcs[k].first, cnt = pcs[k].cnt, in_off = offs[k];
         cudaStream_t s = kstream(k), s_in = pipe_copies ? c->aux[0] : s, s_out = pipe_copies ? c->aux[1] : s;
         while (!ready[k].load(std::memory_order_acquire)) std::this_thread::yield();
-        rc = cudaMemcpyAsync(c->d_in + in_off, c->h_pin + in_off, bytes[k], cudaMemcpyHostToDevice, s_in) == cudaSuccess ? 0 : fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (host to device)");
+        if (direct) { Sink sk{nullptr, c->d_in + in_off, s_in, 0}; pack(first, cnt, &sk); rc = sk.bad ? fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (page-locked caller memory to device)") : 0; }
+        else rc = cudaMemcpyAsync(c->d_in + in_off, c->h_pin + in_off, bytes[k], cudaMemcpyHostToDevice, s_in) == cudaSuccess ? 0 : fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (host to device)");
         if (!rc && pipe_copies && (cudaEventRecord(evs[2 * k], s_in) != cudaSuccess || cudaStreamWaitEvent(s, evs[2 * k], 0) != cudaSuccess)) rc = fail(ZKV_ERR_CUDA, "event (upload done)");
         if (rc) break;
         jobs[k] = job(first, cnt, c->d_in + in_off);
@@ -564,19 +582,20 @@ extern "C" int zkv_groth16_verify_batch(const zkv_vk* vk, const uint8_t* proofs,
     if (!vk || (n && (!proofs || !status_out)) || k < 0 || (n && k && !signals)) return fail(ZKV_ERR_ARG, "zkv_groth16_verify_batch: bad argument");
     if (n == 0) return 0;
     if (k + 1 != vk->n_ic) { memset(status_out, ZKV_VERIFICATION_FAILED, n); return 0; }        // groth16.rs:32
+    const bool direct = n >= 4096 && is_pinned(proofs) && (k == 0 || is_pinned(signals));      // page-locked caller arrays are uploaded in place
     return for_each_device(vk, n, [&](DevCtx* c, size_t b, size_t e) -> int {
         for (size_t s0 = b; s0 < e; s0 += MAX_CHUNK) {
             size_t m = std::min(MAX_CHUNK, e - s0);
             int rc = host_pipeline(c, vk, m, m * (256 + (size_t)k * 32), k,
-                [&](size_t first, size_t cnt, uint8_t* dst) -> size_t {
-                    if (dst) { pcopy(dst, proofs + (s0 + first) * 256, cnt * 256); pcopy(dst + cnt * 256, signals + (s0 + first) * (size_t)k * 32, cnt * (size_t)k * 32); }
+                [&](size_t first, size_t cnt, Sink* dst) -> size_t {
+                    if (dst) { dst->put(0, proofs + (s0 + first) * 256, cnt * 256, true); dst->put(cnt * 256, signals + (s0 + first) * (size_t)k * 32, cnt * (size_t)k * 32, true); }
                     return cnt * (256 + (size_t)k * 32);
                 },
                 [&](size_t first, size_t cnt, uint8_t* d) -> Job {
                     Job j; memset(&j, 0, sizeof j);
                     j.vk = vk; j.n = cnt; j.recs = d; j.stride = 256; j.off = 0; j.mode = SIG_GENERIC; j.sig_a = d + cnt * 256; j.k = k; j.base = c->h_ic0; j.d_status = c->d_out + first;
                     return j;
-                });
+                }, direct);
             if (rc) return rc;
             memcpy(status_out + s0, c->h_out, m);
         }
@@ -682,6 +701,7 @@ static int risc0_batch(const zkv_risc0* h, const uint8_t* seals, const uint64_t*
     if (!offsets_ok(seal_off, n)) return fail(ZKV_ERR_ARG, "seal offsets must be non-decreasing");
     if (!h->initialized) { memset(status_out, ZKV_INVALID_INITIALIZATION, n); return 0; }     // risc0/verifier.rs:84-86, 99-101
     const zkv_vk* vk = h->vk;
+    const bool direct = n >= 4096 && is_pinned(seals) && is_pinned(seal_off) && is_pinned(a32) && (integrity || is_pinned(b32));      // page-locked caller arrays are uploaded in place
     return for_each_device(vk, n, [&](DevCtx* c, size_t b, size_t e) -> int {
         for (size_t s0 = b; s0 < e; s0 += MAX_CHUNK) {
             size_t m = std::min(MAX_CHUNK, e - s0);
@@ -689,15 +709,15 @@ static int risc0_batch(const zkv_risc0* h, const uint8_t* seals, const uint64_t*
             const size_t blob = (size_t)(seal_off[s0 + m] - seal_off[s0]);
             // chunk block layout: [offsets (cnt + 1) x 8][a32 cnt x 32][b32 cnt x 32][seal bytes][slack: k_decode never reads past a record's own length]
             int rc = host_pipeline(c, vk, m, blob + m * (8 + per) + 64 * 8 + 64 * 320, 2,
-                [&](size_t first, size_t cnt, uint8_t* dst) -> size_t {
+                [&](size_t first, size_t cnt, Sink* dst) -> size_t {
                     const size_t i0 = s0 + first, bytes = (size_t)(seal_off[i0 + cnt] - seal_off[i0]);
                     if (!dst) return (cnt + 1) * 8 + cnt * per + bytes + 320;
-                    uint8_t* p = dst;
-                    memcpy(p, seal_off + i0, (cnt + 1) * 8); p += (cnt + 1) * 8;
-                    memcpy(p, a32 + i0 * 32, cnt * 32); p += cnt * 32;
-                    if (!integrity) { memcpy(p, b32 + i0 * 32, cnt * 32); p += cnt * 32; }
-                    pcopy(p, seals + seal_off[i0], bytes); p += bytes;
-                    return (size_t)(p - dst) + 320;
+                    size_t p = 0;
+                    dst->put(p, seal_off + i0, (cnt + 1) * 8); p += (cnt + 1) * 8;
+                    dst->put(p, a32 + i0 * 32, cnt * 32); p += cnt * 32;
+                    if (!integrity) { dst->put(p, b32 + i0 * 32, cnt * 32); p += cnt * 32; }
+                    dst->put(p, seals + seal_off[i0], bytes, true); p += bytes;
+                    return p + 320;
                 },
                 [&](size_t first, size_t cnt, uint8_t* d) -> Job {
                     Job j; memset(&j, 0, sizeof j);
@@ -706,7 +726,7 @@ static int risc0_batch(const zkv_risc0* h, const uint8_t* seals, const uint64_t*
                     j.sig_a = d + (cnt + 1) * 8; j.sig_b = j.sig_a + cnt * 32; j.recs = j.sig_a + cnt * per;
                     j.hc = h->hc; j.base = h->base; j.all_fail = h->all_fail; j.d_status = c->d_out + first;
                     return j;
-                });
+                }, direct);
             if (rc) return rc;
             memcpy(status_out + s0, c->h_out, m);
         }
@@ -766,22 +786,23 @@ extern "C" int zkv_sp1_verify_batch(const zkv_sp1* h, const uint8_t* vkeys, cons
     if (n > 0xffffffffull) return fail(ZKV_ERR_ARG, "batch too large");
     if (!offsets_ok(proof_off, n) || !offsets_ok(pv_off, n)) return fail(ZKV_ERR_ARG, "proof / public-value offsets must be non-decreasing");
     const zkv_vk* vk = h->vk;
+    const bool direct = n >= 4096 && is_pinned(proofs) && is_pinned(proof_off) && is_pinned(pv_off) && is_pinned(vkeys) && is_pinned(public_values);      // page-locked caller arrays are uploaded in place
     return for_each_device(vk, n, [&](DevCtx* c, size_t b, size_t e) -> int {
         for (size_t s0 = b; s0 < e; s0 += MAX_CHUNK) {
             size_t m = std::min(MAX_CHUNK, e - s0);
             const size_t pvb = (size_t)(pv_off[s0 + m] - pv_off[s0]), prb = (size_t)(proof_off[s0 + m] - proof_off[s0]);
             // chunk block layout: [proof offsets (cnt + 1) x 8][public-value offsets (cnt + 1) x 8][vkeys cnt x 32][proof bytes][public values][slack]
             int rc = host_pipeline(c, vk, m, prb + pvb + m * (16 + 32) + 64 * 16 + 64 * 320, 2,
-                [&](size_t first, size_t cnt, uint8_t* dst) -> size_t {
+                [&](size_t first, size_t cnt, Sink* dst) -> size_t {
                     const size_t i0 = s0 + first, pr = (size_t)(proof_off[i0 + cnt] - proof_off[i0]), pv = (size_t)(pv_off[i0 + cnt] - pv_off[i0]);
                     if (!dst) return (cnt + 1) * 16 + cnt * 32 + pr + pv + 320;
-                    uint8_t* p = dst;
-                    memcpy(p, proof_off + i0, (cnt + 1) * 8); p += (cnt + 1) * 8;
-                    memcpy(p, pv_off + i0, (cnt + 1) * 8); p += (cnt + 1) * 8;
-                    memcpy(p, vkeys + i0 * 32, cnt * 32); p += cnt * 32;
-                    pcopy(p, proofs + proof_off[i0], pr); p += pr;
-                    pcopy(p, public_values + pv_off[i0], pv); p += pv;
-                    return (size_t)(p - dst) + 320;
+                    size_t p = 0;
+                    dst->put(p, proof_off + i0, (cnt + 1) * 8); p += (cnt + 1) * 8;
+                    dst->put(p, pv_off + i0, (cnt + 1) * 8); p += (cnt + 1) * 8;
+                    dst->put(p, vkeys + i0 * 32, cnt * 32); p += cnt * 32;
+                    dst->put(p, proofs + proof_off[i0], pr, true); p += pr;
+                    dst->put(p, public_values + pv_off[i0], pv, true); p += pv;
+                    return p + 320;
                 },
                 [&](size_t first, size_t cnt, uint8_t* d) -> Job {
                     const size_t i0 = s0 + first;
@@ -791,7 +812,7 @@ extern "C" int zkv_sp1_verify_batch(const zkv_sp1* h, const uint8_t* vkeys, cons
                     j.sig_a = d + (cnt + 1) * 16; j.recs = j.sig_a + cnt * 32; j.sig_b = j.recs + (size_t)(proof_off[i0 + cnt] - proof_off[i0]);
                     j.base = c->h_ic0; j.d_status = c->d_out + first;
                     return j;
-                });
+                }, direct);
             if (rc) return rc;
             memcpy(status_out + s0, c->h_out, m);
         }
@@ -820,6 +841,13 @@ extern "C" int zkv_sp1_verify_batch_device(const zkv_sp1* h, int device, const v
     return rc;
 }
 
+
+extern "C" void* zkv_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (zkv_device_count() <= 0 || cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); fail(ZKV_ERR_CUDA, "zkv_host_alloc: cudaHostAlloc failed"); return nullptr; }
+    return p;
+}
+extern "C" void zkv_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ------------------------------------------------------------------------------------------ known-answer self test (include/zkv.h)
 extern "C" int zkv_self_test(int device) {

@@ -354,6 +354,33 @@ def g2_check_batch(g2s, n, device=0):
     return out
 
 
+class _PinnedBlock:
+    """owner of one zkv_host_alloc block (freed with the last numpy view of it)"""
+
+    def __init__(self, nbytes):
+        self.ptr = N.lib().zkv_host_alloc(nbytes)
+        if not self.ptr:
+            raise N.ZkvError(N.ZKV_ERR_CUDA, (N.lib().zkv_last_error() or b"").decode())
+
+    def __del__(self):
+        try:
+            N.lib().zkv_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_copy(a):
+    """Copy of a bytes object / numpy array in page-locked memory (zkv_host_alloc).  Batch calls whose inputs are all page-locked upload them
+    in place instead of gathering them into the library's staging buffer first (include/zkv.h)."""
+    src = np.frombuffer(a, dtype=np.uint8) if isinstance(a, (bytes, bytearray)) else np.ascontiguousarray(a)
+    blk = _PinnedBlock(max(src.nbytes, 1))
+    buf = (C.c_uint8 * max(src.nbytes, 1)).from_address(blk.ptr)
+    buf._zkv_owner = blk                                   # the ctypes array keeps the block alive, numpy keeps the ctypes array alive
+    out = np.frombuffer(buf, dtype=np.uint8, count=src.nbytes).view(src.dtype).reshape(src.shape)
+    out[...] = src
+    return out
+
+
 def device_count():
     """number of CUDA devices the library sees (0 without a driver)"""
     return int(N.lib().zkv_device_count())

@@ -678,6 +678,11 @@ def test_large_batch_schedules_agree(Z, gpu, fx):
             v.verify_batch_device(0, d_s.data_ptr(), d_i.data_ptr(), d_j.data_ptr(), n, d_st.data_ptr(), stream.cuda_stream)
         torch.cuda.synchronize()
         dev = d_st.cpu().numpy()
+        # the same call with every input array in page-locked memory: uploaded in place, no staging pass (include/zkv.h zkv_host_alloc)
+        pin = [Z.pinned_copy(np.frombuffer(b"".join(x), dtype=np.uint8)) for x in (b.seals, b.image_ids, b.journals)]
+        poff = Z.pinned_copy(np.arange(n + 1, dtype=np.uint64) * 260)
+        pinned = np.asarray(v.verify_batch_packed(pin[0], poff, pin[1], pin[2], n))
+        assert (host == pinned).all()
         v.tune("overlap", 4); forced4 = np.asarray(v.verify_batch(b.seals, b.image_ids, b.journals))
         v.tune("overlap", 1); serial = np.asarray(v.verify_batch(b.seals, b.image_ids, b.journals))
         v.tune("overlap", 0)
