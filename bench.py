@@ -223,7 +223,7 @@ def main():
         h_blob = Z.pinned_copy(np.frombuffer(b"".join(batch.seals), dtype=np.uint8)); h_off = Z.pinned_copy(np.arange(n + 1, dtype=np.uint64) * 260)
         h_b = Z.pinned_copy(np.frombuffer(b"".join(batch.image_ids), dtype=np.uint8)); h_c = Z.pinned_copy(np.frombuffer(b"".join(batch.journals), dtype=np.uint8))
         e2e_call = lambda out: v.verify_batch_packed(h_blob, h_off, h_b, h_c, n, out)
-        h2d = n * (256 + 64)
+        h2d = h_blob.nbytes + h_off.nbytes + h_b.nbytes + h_c.nbytes      # seals (260 B each), their offsets, image ids, journal digests
         W_M = W_RISC0_M
     else:
         d_a, d_b, d_c = t8(batch.proofs), t8(batch.vkeys), t8(batch.public_values)
@@ -232,7 +232,7 @@ def main():
         h_b = Z.pinned_copy(np.frombuffer(b"".join(batch.vkeys), dtype=np.uint8)); h_c = Z.pinned_copy(np.frombuffer(b"".join(batch.public_values), dtype=np.uint8))
         h_voff = Z.pinned_copy(np.arange(n + 1, dtype=np.uint64) * 96)
         e2e_call = lambda out: v.verify_batch_packed(h_b, h_c, h_voff, h_blob, h_off, n, out)
-        h2d = n * (256 + 32 + 96 + 8)
+        h2d = h_blob.nbytes + h_off.nbytes + h_b.nbytes + h_c.nbytes + h_voff.nbytes
         W_M = W_SP1_M
     d_st = torch.full((n,), 255, dtype=torch.uint8, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
