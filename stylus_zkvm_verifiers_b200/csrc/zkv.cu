@@ -430,9 +430,9 @@ static void pcopy(void* dst, const void* src, size_t n) {
     int parts = (int)std::min<size_t>(4, n / MIN);
     if (parts <= 1) { memcpy(dst, src, n); return; }
     std::vector<std::thread> th;
-    const size_t per = (n / parts + 63) / 64 * 64;
-    for (int t = 1; t < parts; t++) { size_t o = per * t, l = std::min(per, n - o); th.emplace_back([=]() { memcpy((uint8_t*)dst + o, (const uint8_t*)src + o, l); }); }
-    memcpy(dst, src, per);
+    const size_t per = ((n + parts - 1) / parts + 63) / 64 * 64;      // CEILING of n / parts: parts x per >= n, the slices cover every byte
+    for (int t = 1; t < parts; t++) { size_t o = per * t; if (o >= n) break; size_t l = std::min(per, n - o); th.emplace_back([=]() { memcpy((uint8_t*)dst + o, (const uint8_t*)src + o, l); }); }
+    memcpy(dst, src, std::min(per, n));
     for (auto& t : th) t.join();
 }
 

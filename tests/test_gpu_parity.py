@@ -738,3 +738,22 @@ def test_async_device_calls_share_the_workspace_safely(Z, gpu, fx):
         v.verify_batch_device(0, dB[0].data_ptr(), dB[1].data_ptr(), dB[2].data_ptr(), len(wantB), stB.data_ptr(), None)
     torch.cuda.synchronize()
     assert stB.cpu().numpy().tolist() == wantB.tolist()
+
+
+def test_staging_copy_covers_every_byte(Z, gpu, fx):
+    """Regression (round 2): large blocks are gathered into the pinned staging buffer by several copy threads; slicing by floor(n / parts)
+    once left the last n mod parts bytes of a chunk's seal blob uncopied whenever floor(n / parts) was a multiple of 64 - five valid proofs in
+    the 10^7-proof campaign came back rejected, caught by the committed oracle digests.  Here chunk 0's blob is 16384 x 260 + 1 bytes (one seal
+    a byte too long), i.e. exactly that case, and the staging buffer is dirtied by a different batch first."""
+    from stylus_zkvm_verifiers_b200 import synth as S
+    vk = S.make_vk(gpu, 0, 6, 0xB2000001)
+    v = Z.RiscZeroVerifier(Z.VerificationKey(0, vk.alpha, vk.beta, vk.gamma, vk.delta, vk.ic)); v.initialize(fx["control_root"], fx["bn254_control_id"])
+    n = 1 << 16
+    mk = lambda seed: S.make_risc0_batch(gpu, vk, v.get_selector(), fx["control_root"], fx["bn254_control_id"], fx["sys0"], n, seed, pool=256)
+    dirty, b = mk(0xB2000061), mk(0xB2000062)
+    assert (np.asarray(v.verify_batch(dirty.seals, dirty.image_ids, dirty.journals)) == 0).all()
+    for odd in (5, 16384 + 9, 3 * 16384 + 1):              # one over-long seal in chunks 0, 1 and 3: their blobs have odd lengths
+        b.seals[odd] = b.seals[odd] + b"\\x00"
+    st = np.asarray(v.verify_batch(b.seals, b.image_ids, b.journals))
+    want = np.zeros(n, dtype=np.uint8); want[[5, 16384 + 9, 3 * 16384 + 1]] = 2          # InvalidProofData for the three, every other proof valid
+    assert (st == want).all(), np.nonzero(st != want)[0][:10]
