@@ -227,6 +227,7 @@ __device__ __noinline__ bool g2v_in_subgroup(fp2 qx, fp2 qy) {
 #else
 static inline bool g2v_in_subgroup(fp2 qx, fp2 qy) { return g2_in_subgroup(qx, qy); }
 #endif
+// (four blocks per SM at 128 registers were measured: the spills cost more than the second wave they save, 2.80 against 2.59 ms per 2^16)
 __global__ void k_g2_check(int n, const fp2* bx, const fp2* by, uint8_t* flags) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
