@@ -59,6 +59,13 @@ static inline void lz_hi_chain(uint32_t* r, const uint32_t* x, const uint32_t* n
 }
 static inline void lz_addw_hi(uint32_t* r, const uint32_t* x, const uint32_t* n) { lz_hi_chain(r, x, n, 0, "addw_hi carry"); }
 static inline void lz_subw_hi(uint32_t* r, const uint32_t* x, const uint32_t* n) { lz_hi_chain(r, x, n, 1, "subw_hi borrow"); }
+static inline void lz_shl3w(uint32_t* r, const uint32_t* x) {
+    if (x[15] >> 29) lz_die("shl3w overflow");
+    uint32_t t[16];
+    t[0] = x[0] << 3;
+    for (int i = 1; i < 16; i++) t[i] = (x[i] << 3) | (x[i - 1] >> 29);
+    for (int i = 0; i < 16; i++) r[i] = t[i];
+}
 static inline void lz_csub_top(uint32_t* r, const uint32_t* x, const uint32_t* k, int n) {
     uint32_t t[8]; uint64_t bo = 0; int lo = n - 8;
     for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)x[lo + i] - k[i] - bo; t[i] = (uint32_t)d; bo = (d >> 63) & 1; }

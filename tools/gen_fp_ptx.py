@@ -91,6 +91,12 @@ class Prog:
             if op == "and":
                 reg[dst] = src[0] & src[1]
                 continue
+            if op == "shf.l":         # funnel shift left: the upper 32 bits of (hi:lo) << n  (src = lo, hi, n)
+                reg[dst] = (((src[1] << 32) | src[0]) << src[2] >> 32) & MASK
+                continue
+            if op == "shl":
+                reg[dst] = (src[0] << src[1]) & MASK
+                continue
             if op == "mov":
                 reg[dst] = src[0]
                 continue
@@ -122,7 +128,7 @@ class Prog:
                 lines.append("setp.eq.u32 q, %s, 0;" % fmt(src[2]))
                 lines.append("selp.u32 %s, %s, %s, q;" % (fmt(dst), fmt(src[0]), fmt(src[1])))
                 continue
-            pop = {"and": "and.b32", "mov": "mov.u32"}.get(op, op + ".u32")
+            pop = {"and": "and.b32", "mov": "mov.u32", "shf.l": "shf.l.wrap.b32", "shl": "shl.b32"}.get(op, op + ".u32")
             lines.append("%s %s, %s;" % (pop, fmt(dst), ", ".join(fmt(s) for s in src)))
         body = "\n".join('        "%s\\n\\t"' % l for l in lines)
         outs = ", ".join('"=r"(%s)' % self._c(o) for o in self.outs)
@@ -494,6 +500,15 @@ def gen_hi(name, op):
     return p
 
 
+def gen_shl3w():
+    """r = 8 x for a 16-limb x < 2^509: sixteen independent funnel shifts instead of three dependent 16-limb doublings (the 9 x of xi = 9 + u)."""
+    p = Prog("lz_shl3w", nm("x", 16), nm("r", 16))
+    p.emit("shl", "r0", "x0", 3)
+    for k in range(1, 16):
+        p.emit("shf.l", "r%d" % k, "x%d" % (k - 1), "x%d" % k, 3)
+    return p
+
+
 def gen_csub(name, n):
     """the top 8 limbs of an n-limb x (n = 8 or 16) minus the 8-limb constant k if that does not borrow, else unchanged."""
     p = Prog(name, nm("x", n) + nm("k", 8), nm("r", n))
@@ -509,7 +524,7 @@ def gen_csub(name, n):
 
 def leaf_progs():
     return [gen_mulw(), gen_redc_nf(), gen_chain("lz_add8", "add", 8), gen_chain("lz_sub8", "sub", 8), gen_chain("lz_addw", "add", 16),
-            gen_chain("lz_subw", "sub", 16), gen_addhi(), gen_csub("lz_csubw", 16), gen_csub("lz_csub8", 8), gen_hi("lz_addw_hi", "add"), gen_hi("lz_subw_hi", "sub"), gen_mulw2()]
+            gen_chain("lz_subw", "sub", 16), gen_addhi(), gen_csub("lz_csubw", 16), gen_csub("lz_csub8", 8), gen_hi("lz_addw_hi", "add"), gen_hi("lz_subw_hi", "sub"), gen_mulw2(), gen_shl3w()]
 
 
 def check_leaves(iters=600):
@@ -521,7 +536,7 @@ def check_leaves(iters=600):
         for c, (x, n) in kw.items():
             inp.update({"%s%d" % (c, i): v for i, v in lim(x, n).items()})
         return val(prog.run(inp))
-    mulw, redc, add8, sub8, addw, subw, addhi, csubw, csub8, addw_hi, subw_hi, mulw2 = leaf_progs()
+    mulw, redc, add8, sub8, addw, subw, addhi, csubw, csub8, addw_hi, subw_hi, mulw2, shl3w = leaf_progs()
     Bw = P << 256
     for it in range(iters):
         a, b = rnd.getrandbits(256), rnd.getrandbits(256)
@@ -542,6 +557,8 @@ def check_leaves(iters=600):
         assert run(add8, a=(x, 8), b=(y, 8)) == x + y and run(sub8, a=(y, 8), b=(x, 8)) == y - x
         x, y = sorted((rnd.getrandbits(511), rnd.getrandbits(511)))
         assert run(addw, a=(x, 16), b=(y, 16)) == x + y and run(subw, a=(y, 16), b=(x, 16)) == y - x
+        xs = rnd.getrandbits(509) if it > 3 else [0, (1 << 509) - 1, 1, (1 << 508) + 5][it]
+        assert run(shl3w, x=(xs, 16)) == xs << 3
         nn = rnd.getrandbits(255)
         assert run(addw_hi, x=(x, 16), n=(nn, 8)) == x + (nn << 256)
         big = x | (1 << 511)
@@ -564,6 +581,7 @@ LEAF_SIGS = {
     "lz_csub8": "uint32_t* r, const uint32_t* x, const uint32_t* k",
     "lz_addw_hi": "uint32_t* r, const uint32_t* x, const uint32_t* n", "lz_subw_hi": "uint32_t* r, const uint32_t* x, const uint32_t* n",
     "lz_mulw2": "uint32_t* w, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d",
+    "lz_shl3w": "uint32_t* r, const uint32_t* x",
 }
 
 

@@ -267,9 +267,18 @@ class Gen:
         self.emit("lz_addw(%s, %s, %s);" % (w.name, a.name, a.name))
         return w
 
+    def shl3w(self, a):
+        """8 a by sixteen independent funnel shifts (no carry chain)"""
+        a = self.ensure(a, LIM // 8 - 1)
+        self.stats["wide_addsub"] += 1
+        w = self._w({k: 8 * c for k, c in a.lin.items()}, 8 * a.off, [8 * v for v in a.vals])
+        self.emit("lz_shl3w(%s, %s);" % (w.name, a.name))
+        return w
+
     def mul9(self, x):
-        d = self.dblw(self.dblw(self.dblw(x)))
-        return self.addw(d, x)
+        if x.hi() < LIM // 8:                      # 8 x fits: sixteen independent funnel shifts
+            return self.addw(self.shl3w(x), x)
+        return self.addw(self.dblw(self.dblw(self.dblw(x))), x)      # else three doublings, conditionally reduced on the way
 
     def mul_xi(self, re, im):
         """(re + im u)(9 + u) = (9 re - im) + (9 im + re) u"""

@@ -256,8 +256,17 @@ class Gen2:
         self.emit("lz_addw(%s, %s, %s);" % (w.name, a.name, a.name))
         return w
 
+    def shl3w(self, a):
+        a = self.ensure(a, LIM // 8 - 1)
+        self.stats["wide_addsub"] += 1
+        w = self._w([{k: 8 * c for k, c in a.lin[l].items()} for l in range(2)], 8 * a.off, [[8 * v for v in a.vals[l]] for l in range(2)])
+        self.emit("lz_shl3w(%s, %s);" % (w.name, a.name))
+        return w
+
     def mul9(self, x):
-        return self.addw(self.dblw(self.dblw(self.dblw(x))), x)
+        if x.hi() < LIM // 8:                      # 8 x fits: sixteen independent funnel shifts
+            return self.addw(self.shl3w(x), x)
+        return self.addw(self.dblw(self.dblw(self.dblw(x))), x)      # else three doublings, conditionally reduced on the way
 
     def xchg(self, x):
         """the other lane's copy of a wide value (16 shuffles)"""
