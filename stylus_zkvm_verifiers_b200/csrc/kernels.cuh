@@ -396,6 +396,7 @@ __global__ void __launch_bounds__(ZKV_HTPB_FE, ZKV_MINBLOCKS_FE) k_final_exp_sta
 // between segments / stages travels through HBM exactly as in the round-1 kernels.  `sl` must have room for 4 Fp per LAUNCHED thread
 // (surplus threads of the last block park their slopes behind the batch).
 #define LZ_SMEM_BYTES (LZ_SLOTS * 32 * LZ_NT)
+#define LZ_SMEM_MILLER (LZ_SMEM_BYTES + 1024)      /* + the per-warp line staging areas of lz_fixed_lines: 2 x (112 KB + 1 KB + 1 KB reserved) = the SM's 228 KB */
 // slopes of the two fixed pairs (g1_slopes2) written to sl[0..3] = xy0, xy1, iy0, iy1; out of line so that its arrays have a frame of their own
 __device__ __noinline__ void lz_slopes_to(fp* sl, const fp* x1, const fp* y1, const fp* x2, const fp* y2, bool off1, bool off2) {
     fp x12[2] = {*x1, *x2}, y12[2] = {*y1, *y2}, xy[2], iy[2];

@@ -227,14 +227,50 @@ struct LzMillerIn {                 // everything a thread reads per step comes 
     const nline_t* nt[2];           // normalised line tables of the two fixed G2 points
     bool var_off;
 };
-// the two fixed pairs' lines number li: f *= 1 + n3 (xP/yP) w + n4 (1/yP) v w for each
-LZ_INL void lz_fixed_lines(const LzMillerIn& in, int li, uint32_t tid) {
+// The two fixed pairs' lines number li: f *= 1 + n3 (xP/yP) w + n4 (1/yP) v w for each.
+// Their table entries (2 x 128 bytes per step, the same for every proof) are STAGED IN SHARED MEMORY, one 256-byte area per warp behind the
+// slots (the kilobyte per block that 2 x 112 KB of slots leave of the SM's 228 KB): sixteen lanes fetch 16 bytes each of the NEXT step's
+// entries at the start of a step, the loads are in flight during the step's two line products, and the values are parked in the staging
+// area at its end, so the loop no longer waits for L2 (the long-scoreboard share of the loop body).  Warp-private, so
+// `__syncwarp` is all the ordering it needs.  `have` says whether the area already holds entry li (false at the start of a segment).
+#define LZ_STAGE (LZ_SLOTS * LZ_SLOT)            /* uint4 index of the staging areas: 16 uint4 per warp */
+#if defined(__CUDACC__)
+LZ_INL uint32_t lz_stage_base() { return LZ_STAGE + (lz_tid() >> 5) * 16; }
+LZ_INL uint4 lz_line_fetch(const nline_t* const nt[2], int li) {
+    const uint32_t lane = lz_tid() & 31;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (lane < 16) v = ((const uint4*)(nt[lane >> 3] + li))[lane & 7];
+    return v;
+}
+LZ_INL void lz_line_stage(uint4 v) {
+    const uint32_t lane = lz_tid() & 31;
+    __syncwarp();
+    if (lane < 16) lz_sm[lz_stage_base() + lane] = v;
+    __syncwarp();
+}
+LZ_INL nline_t lz_line_staged(int j) {
+    nline_t nl; uint4* w = (uint4*)&nl;
+    for (int k = 0; k < 8; k++) w[k] = lz_sm[lz_stage_base() + 8 * j + k];
+    return nl;
+}
+#else
+struct lz_stage_t { nline_t e[2]; };
+static lz_stage_t lz_stage_host;
+LZ_INL lz_stage_t lz_line_fetch(const nline_t* const nt[2], int li) { lz_stage_t v; v.e[0] = nt[0][li]; v.e[1] = nt[1][li]; return v; }
+LZ_INL void lz_line_stage(const lz_stage_t& v) { lz_stage_host = v; }
+LZ_INL nline_t lz_line_staged(int j) { return lz_stage_host.e[j]; }
+#endif
+LZ_INL void lz_fixed_lines(const LzMillerIn& in, int li, uint32_t tid, bool& have) {
+    if (!have) lz_line_stage(lz_line_fetch(in.nt, li));
+    const int nx = li + 1 < ZKV_LINES_PER_G2 ? li + 1 : li;
+    auto next = lz_line_fetch(in.nt, nx);
     for (int j = 0; j < 2; j++) {
-        nline_t nl = in.nt[j][li];
+        nline_t nl = lz_line_staged(j);
         lz_st2(tid + LZ_L * LZ_SLOT, f2v_mul_fp(nl.n3, in.sl[j]));
         lz_st2(tid + (LZ_L + 2) * LZ_SLOT, f2v_mul_fp(nl.n4, in.sl[2 + j]));
         lz_mul_nline(tid + LZ_F * LZ_SLOT, tid + LZ_T * LZ_SLOT, tid + LZ_L * LZ_SLOT);
     }
+    lz_line_stage(next); have = nx == li + 1;
 }
 // digits d_hi .. d_lo of the loop (the two Frobenius lines with the last segment); f and R must be in the slots (f = 1, R = Q before the first).
 // OUT OF LINE, arguments by value: inlined into a kernel that also holds arrays for the slope computation, nvcc 12.9 merged stack slots of
@@ -242,18 +278,18 @@ LZ_INL void lz_fixed_lines(const LzMillerIn& in, int li, uint32_t tid) {
 // section 5, seen again on the GPU as an illegal address); in its own frame the block lives in registers.
 LZ_FN2 void lz_miller_norm_seg(LzMillerIn in, int d_hi, int d_lo, bool last) {
     const uint32_t tid = lz_tid(), F = tid + LZ_F * LZ_SLOT, T = tid + LZ_T * LZ_SLOT, RR = tid + LZ_R * LZ_SLOT, L = tid + LZ_L * LZ_SLOT;
-    int li = 0;
+    int li = 0; bool have = false;
     for (int d = ZKV_ATE_NAF_LEN - 2; d > d_hi; d--) li += 1 + (C_ATE_NAF[d] != 0);
     for (int d = d_hi; d >= d_lo; d--) {
         if (d != ZKV_ATE_NAF_LEN - 2) lz_f12sqr(F, T);
         { fp2 a = lz_line_dbl(RR, L, in.px0, in.py0, in.var_off); lz_mul_line(F, T, L, a); }
-        lz_fixed_lines(in, li, tid);
+        lz_fixed_lines(in, li, tid, have);
         li++;
         const int dg = C_ATE_NAF[d];
         if (dg) {
             fp2 y = *in.qy; if (dg < 0) y = f2v_neg(y);
             { fp2 a = lz_line_add(RR, L, *in.qx, y, in.px0, in.py0, in.var_off); lz_mul_line(F, T, L, a); }
-            lz_fixed_lines(in, li, tid);
+            lz_fixed_lines(in, li, tid, have);
             li++;
         }
     }
@@ -262,7 +298,7 @@ LZ_FN2 void lz_miller_norm_seg(LzMillerIn in, int d_hi, int d_lo, bool last) {
         fp2 xs = *in.qx, ys = *in.qy; g2_frob_affine(xs, ys, s);
         if (s == 2) ys = f2v_neg(ys);
         { fp2 a = lz_line_add(RR, L, xs, ys, in.px0, in.py0, in.var_off); lz_mul_line(F, T, L, a); }
-        lz_fixed_lines(in, li, tid);
+        lz_fixed_lines(in, li, tid, have);
         li++;
     }
 }

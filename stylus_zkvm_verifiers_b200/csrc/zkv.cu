@@ -161,7 +161,7 @@ static int vk_build_on(zkv_vk* vk, DevCtx* c) {
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_busy, cudaEventDisableTiming));
     for (auto& e : c->ev_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CK(cudaFuncSetAttribute(k_miller_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_miller_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_MILLER));
     CK(cudaFuncSetAttribute(k_final_exp_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_pairing_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_BYTES));
     int nt = vk->n_ic - 1;
@@ -333,7 +333,7 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
         const int S = (segs > 1 && !mono) ? segs : 1;
         for (int k = 0; k < S; k++) {
             int hi = top - (top + 1) * k / S, lo = top - (top + 1) * (k + 1) / S + 1;
-            k_miller_lz<<<nblk(m, LZ_NT), LZ_NT, LZ_SMEM_BYTES, s>>>(m, a, flags, c->f + o, c->rst + o, c->sl + 4 * o, hi, lo, k == 0, k == S - 1);
+            k_miller_lz<<<nblk(m, LZ_NT), LZ_NT, LZ_SMEM_MILLER, s>>>(m, a, flags, c->f + o, c->rst + o, c->sl + 4 * o, hi, lo, k == 0, k == S - 1);
             DBG("k_miller_lz");
         }
         nl += S - 1;
@@ -1017,11 +1017,11 @@ extern "C" int zkv_fp12_op_batch(int op, const uint8_t* a, const uint8_t* b, siz
     // second output buffer of with_scratch doubles as the kernel's per-thread scratch (7 Fp12 per launched thread); nothing is copied back from it
     if (zkv_device_count() <= device || device < 0) return fail(ZKV_ERR_CUDA, "no such CUDA device (this library has no CPU path)");
     CK(cudaSetDevice(device));
-    CK(cudaFuncSetAttribute(k_lz_fp12_op, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_lz_fp12_op, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_MILLER));
     fp12* scratch = nullptr; CK(cudaMalloc(&scratch, launched * 7 * sizeof(fp12)));
     nline_t* ztab = nullptr; CK(cudaMalloc(&ztab, ZKV_LINES_PER_G2 * sizeof(nline_t))); CK(cudaMemset(ztab, 0, ZKV_LINES_PER_G2 * sizeof(nline_t)));
     int rc = with_scratch(device, a, n * 384, b ? b : &dummy, b ? n * 384 : 0, out, n * 384, &dummy, 0,
-                          [&](uint8_t* d0, uint8_t* d1, uint8_t* o0, uint8_t*) { k_lz_fp12_op<<<nblk(n, LZ_NT), LZ_NT, LZ_SMEM_BYTES>>>((int)n, k, d0, b ? d1 : nullptr, o0, scratch, ztab); });
+                          [&](uint8_t* d0, uint8_t* d1, uint8_t* o0, uint8_t*) { k_lz_fp12_op<<<nblk(n, LZ_NT), LZ_NT, LZ_SMEM_MILLER>>>((int)n, k, d0, b ? d1 : nullptr, o0, scratch, ztab); });
     cudaFree(scratch); cudaFree(ztab);
     return rc;
 }
@@ -1136,7 +1136,7 @@ extern "C" long long zkv_wave_proofs(int device, int kernel) {
     int per_sm = 0;
     cudaError_t e; int tpb;
     switch (kernel) {
-        case 0: tpb = LZ_NT; cudaFuncSetAttribute(k_miller_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_BYTES); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_miller_lz, LZ_NT, LZ_SMEM_BYTES); break;
+        case 0: tpb = LZ_NT; cudaFuncSetAttribute(k_miller_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_MILLER); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_miller_lz, LZ_NT, LZ_SMEM_MILLER); break;
         case 1: tpb = LZ_NT; cudaFuncSetAttribute(k_final_exp_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SMEM_BYTES); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_final_exp_lz, LZ_NT, LZ_SMEM_BYTES); break;
         case 2: tpb = ZKV_HTPB_MILLER; e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_miller_norm, ZKV_HTPB_MILLER, 0); break;
         case 3: tpb = ZKV_HTPB_FE; e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_final_exp, ZKV_HTPB_FE, 0); break;
