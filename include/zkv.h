@@ -168,7 +168,7 @@ int zkv_last_stage_ms(const void* handle_vk, int device, float* out, int cap);
  *     batches under 8192 proofs are never cut; 1 = one chain on the main stream with the per-stage events zkv_last_stage_ms reads.
  *   ZKV_TUNE_NORMALISED_LINES (0/1, default 1): verification path uses the per-key normalised gamma / delta line tables (first
  *     coefficient scaled to 1 by a subfield element: 10 instead of 13 Fp2 products per line); 0 = the unscaled lines of the pairing service.
- *   ZKV_TUNE_MILLER_SEGMENTS (1..16, default 8): chunked batches run the Miller loop as that many kernels (f, R carried in HBM).
+ *   ZKV_TUNE_MILLER_SEGMENTS (1..16, default 4): chunked batches run the Miller loop as that many kernels (f, R carried in HBM).
  *   ZKV_TUNE_FINAL_EXP_STAGES (0/1, default 1): chunked batches run the final exponentiation as four stage kernels (state in HBM).
  *   ZKV_TUNE_LAYOUT (0/1, default 1): 1 = shared-memory-resident lazily reduced Miller / final-exponentiation kernels (two blocks of
  *     128 threads per SM, 28 Fp slots of shared memory per proof), 0 = the round-1 kernels (thread stack, three / two blocks per SM);

@@ -86,7 +86,7 @@ struct DevCtx {
 struct Tuning {
     std::atomic<int> overlap_chunks{0};     // a device batch is cut into this many kernel chains on side streams; 0 = automatic (chunk_count)
     std::atomic<int> normalised_lines{1};   // verification path: gamma / delta lines scaled to (1, n3, n4)
-    std::atomic<int> miller_segments{8};    // chunked batches: segment kernels per Miller loop (state in HBM between them)
+    std::atomic<int> miller_segments{4};    // chunked batches: segment kernels per Miller loop (state in HBM between them); 4 measured best (profiles/r2_chunk_sweep.txt)
     std::atomic<int> final_exp_stages{1};   // chunked batches: the final exponentiation as four stage kernels
     std::atomic<int> layout{1};             // 1: shared-memory-resident lazily reduced kernels (lazy.cuh); 0: the round-1 thread-stack kernels
 };
