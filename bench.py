@@ -259,7 +259,7 @@ def main():
         v.tune("layout", args.layout)
     chunks, layout = v.tune("overlap"), v.tune("layout")
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    n_chunks = chunks if chunks else (1 if n >= 2 * sms * 256 else max(1, -(-n // (sms * 128))))      # automatic policy of csrc/zkv.cu chunk_count
+    n_chunks = chunks if chunks else (1 if n < sms * 128 else 4)      # automatic policy of csrc/zkv.cu chunk_count
     for _ in range(max(args.warmup, 3)):
         launch(d_st, sp)
     torch.cuda.synchronize()
@@ -339,7 +339,7 @@ def main():
         "dtype": "u256 (8x32-bit Montgomery limbs, IMAD.WIDE.U32)", "data": "synthetic",
         "config": workload_config(args.shape, n),
         "execution": {"l2": "flushed between timed steps (256 MiB fill)", "layout": "shared-memory-resident lazily reduced kernels" if layout else "round-1 thread-stack kernels",
-                      "overlap": "%d chunks per device batch on side streams%s (stage_ms: serial single-chain pass over all proofs; roofline: serial single-chain launches of a whole number of waves)" % (n_chunks, "" if chunks else " (automatic: half-wave pieces below two waves of the heavy kernels, one chain above)")},
+                      "overlap": "%d chunks per device batch on side streams%s (stage_ms: serial single-chain pass over all proofs; roofline: serial single-chain launches of a whole number of waves)" % (n_chunks, "" if chunks else " (automatic; front kernels first, then per chunk 4 Miller segment + 4 final-exponentiation stage kernels)")},
         "e2e": {"value": total / e2e_s, "unit": "verifies/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": n},
         "gpu_launches": launches,
         "stage_ms": stage_sum,

@@ -161,11 +161,11 @@ int zkv_last_stage_ms(const void* handle_vk, int device, float* out, int cap);
 /* Tuning of ONE key handle (every verifier handle built on that key sees it; there is no process-wide setting).  `handle_vk` is a
  * zkv_vk* or what zkv_risc0_vk / zkv_sp1_vk return.  Returns the previous value (value = ZKV_TUNE_QUERY only reads it), < 0 on error.
  * None of the options changes a status byte or a final-exponentiation value (tests/test_gpu_parity.py).
- *   ZKV_TUNE_OVERLAP (0..64, default 0 = automatic): a device batch is cut into that many pieces whose kernel chains run on side streams,
- *     so the partial last wave of one kernel is back-filled by blocks of another.  Automatic: pieces of half a wave of the heavy kernels
- *     (SMs x 128 proofs) for batches below two waves (2^16 proofs on a B200: four pieces), ONE chain of one-launch kernels above (measured
- *     faster from about two waves on; host-buffer calls then still pipeline packing, upload and download in whole-wave pieces);
- *     batches under 8192 proofs are never cut; 1 = one chain on the main stream with the per-stage events zkv_last_stage_ms reads.
+ *   ZKV_TUNE_OVERLAP (0..64, default 0 = automatic): a device batch is cut into that many pieces whose heavy kernels (Miller segments,
+ *     final-exponentiation stages) run on side streams, so the partial last wave of one kernel is back-filled by blocks of another; the
+ *     front kernels of all pieces run first.  Automatic: one chain below half a wave of the heavy kernels (SMs x 128 proofs), four pieces
+ *     above (measured best at every size from 2^16 to 2^20); batches under 8192 proofs are never cut; 1 = one chain on the main stream with
+ *     the per-stage events zkv_last_stage_ms reads.
  *   ZKV_TUNE_NORMALISED_LINES (0/1, default 1): verification path uses the per-key normalised gamma / delta line tables (first
  *     coefficient scaled to 1 by a subfield element: 10 instead of 13 Fp2 products per line); 0 = the unscaled lines of the pairing service.
  *   ZKV_TUNE_MILLER_SEGMENTS (1..16, default 4): chunked batches run the Miller loop as that many kernels (f, R carried in HBM).

@@ -360,23 +360,21 @@ static int enqueue_chain(DevCtx* c, const Job& j, size_t jo, size_t o, int m, cu
     CK(cudaGetLastError());
     return 0;
 }
-// Chunks of a device batch.  Measured on B200 (tools/sweep_chunks.sh, profiles/r2_chunk_sweep.txt): kernel chains of several chunks running
-// side by side on different streams only pay when the batch is a small number of waves of the heavy kernels (2 resident blocks of 128
-// threads per SM: one wave = SMs x 256 proofs).  2^16 proofs are 1.73 waves: one chain pays for two full waves (35.0 ms), four half-wave
-// chunks whose segment / stage kernels back-fill each other's partial waves take 33.8 ms.  From about two waves on, one serial chain of
-// one-launch kernels is faster than any chunking (2^17: 68.4 against 69.2 ms, 2^18: 126 against 141 ms, 2^20: 504 against 612 ms, i.e. 2.08 M
-// against 1.71 M verifies/s): co-scheduled kernels of different stages take each other's block slots, and the light kernels (vk_x, the
-// G2 check) run at a fraction of their own occupancy between the heavy blocks.  Automatic (setting 0): half-wave chunks below two waves,
-// one chain above.  A positive setting forces that many chunks.
+// Chunks of a device batch (measured on B200: tools/sweep_chunks.sh, tools/sweep_segments.sh, profiles/r2_chunk_sweep.txt).  The heavy kernels
+// hold 2 blocks of 128 threads per SM (one wave = SMs x 256 proofs), and a batch is rarely a whole number of waves: 2^16 proofs are 1.73.
+// Cut into FOUR chunks whose Miller loops run as 4 segment kernels and whose final exponentiations run as 4 stage kernels on four side
+// streams, the block scheduler back-fills one chunk's partial wave with another chunk's blocks; the front kernels (decode, hashing, vk_x, G2
+// check) run before all of that, over the whole batch, because interleaved with heavy blocks they run at a fraction of their occupancy and
+// take block slots from them.  On the final build this schedule wins at every size from half a wave up (2^16: 31.3 ms against 35.0 for one
+// chain; 2^17: 60.6 against 62.7; 2^18: 121.5 against 123.8; 2^20: 488 against 499 ms); more chunks are worse at every size.  (While the front
+// kernels still ran inside the chunks and the Miller loop had 8 segments, one serial chain was the faster schedule from two waves on, and for
+// a while it was the automatic choice there.)  Automatic (setting 0): one chain below half a wave, four chunks above; a positive setting forces
+// that many chunks (1 = one chain on the main stream with the per-stage events zkv_last_stage_ms reads).
 static size_t wave_proofs_of(const DevCtx* c) { return (size_t)c->sms * 2 * ZKV_HTPB; }
-// a partial last wave worth running as a chain of its own beside the whole waves: not so small that it does not matter, not so full that there is little to fill
-static bool worth_splitting(size_t rem, size_t wave) { return rem >= wave / 8 && rem <= wave * 5 / 8; }
 static int chunk_count(const DevCtx* c, size_t n, int setting) {
     if (n < (size_t)8192) return 1;
     if (setting >= 1) return setting;
-    if (n >= 2 * wave_proofs_of(c)) return 1;
-    const size_t half = wave_proofs_of(c) / 2;
-    return (int)std::max<size_t>(1, (n + half - 1) / half);
+    return n < wave_proofs_of(c) / 2 ? 1 : 4;
 }
 // Fork `chunks` side streams off `main`, run fn(chunk_begin, chunk_len, stream) on them round-robin, join back into `main`.
 // Chunk boundaries are multiples of the heavy kernels' block size so no chunk carries a second partial block.
@@ -402,21 +400,6 @@ static int run_verify(DevCtx* c, const Job& j) {
     if (c->busy && (j.n > c->cap || j.n > c->fes_cap || j.n * (size_t)ns * 8 > c->scal_words)) { CK(cudaEventSynchronize(c->ev_busy)); c->busy = false; }   // growing frees buffers an earlier asynchronous call may still use
     rc = ctx_reserve(c, j.n, (size_t)ns * 8); if (rc) return rc;
     int chunks = chunk_count(c, j.n, j.vk->tune.overlap_chunks.load());
-    {   // from two waves on (automatic setting): the whole waves as ONE chain of one-launch kernels, the partial last wave as a second chain
-        // beside it, whose blocks fill the slots the first chain's kernels leave at their ends (2^17 proofs = 3.46 waves: 64.4 against 68.9 ms)
-        const size_t wave = wave_proofs_of(c), whole = j.n / wave * wave, rem = j.n - whole;
-        if (chunks == 1 && j.vk->tune.overlap_chunks.load() == 0 && j.n >= 2 * wave && worth_splitting(rem, wave) && !(j.all_fail || !j.vk->valid)) {
-            rc = enqueue_chain(c, j, 0, 0, (int)j.n, c->stream, false, false, 1); if (rc) return rc;
-            CK(cudaEventRecord(c->ev_fork, c->stream));
-            const size_t off[2] = {0, whole}, len[2] = {whole, rem};
-            for (int k = 0; k < 2; k++) {
-                CK(cudaStreamWaitEvent(c->aux[k], c->ev_fork, 0));
-                rc = enqueue_chain(c, j, off[k], off[k], (int)len[k], c->aux[k], false, true, 2); if (rc) return rc;
-                CK(cudaEventRecord(c->ev_join[k], c->aux[k])); CK(cudaStreamWaitEvent(c->stream, c->ev_join[k], 0));
-            }
-            return 0;
-        }
-    }
     if (chunks <= 1) return enqueue_chain(c, j, 0, 0, (int)j.n, c->stream, true);
     if (j.all_fail || !j.vk->valid) return enqueue_chain(c, j, 0, 0, (int)j.n, c->stream, false);
     // the front kernels run once over the whole batch (at their own full occupancy), only the heavy kernels are chunked over the side streams
@@ -462,28 +445,16 @@ template <class Pack, class MakeJob>
 static int host_pipeline(DevCtx* c, const zkv_vk* vk, size_t m, size_t in_bytes, int ns, Pack pack, MakeJob job, bool direct = false) {
     if (c->busy) { CK(cudaEventSynchronize(c->ev_busy)); c->busy = false; }      // a host call blocks anyway: wait out an earlier asynchronous device call here
     int rc = ctx_reserve(c, m, (size_t)ns * 8); if (rc) return rc;
-    // Pieces of the batch, in upload order.  Below two waves (or with a forced chunk count): `chunks` equal pieces, each with its own side
-    // stream; every piece runs its front kernels first, side by side with the others', then the heavy ones (interleaved with heavy blocks,
-    // vk_x and the G2 check run at a fraction of their occupancy and take block slots from them).  From two waves on (automatic setting): the
-    // KERNELS of all whole waves run back to back on the main stream as one-launch kernels, in pieces of up to four waves whose packing, upload
-    // (side stream 0) and status download (side stream 1) overlap the kernels of the pieces around them; the partial last wave is a piece of
-    // its own, uploaded first, whose chain runs beside the main one (side stream 2) and fills the block slots its kernels leave at their ends.
-    struct Piece { size_t first, cnt; int lane; };      // lane 0: side stream per piece, 1: main stream (piped), 2: the remainder's stream (piped)
+    // Pieces of the batch, in upload order: `chunks` equal pieces (multiples of the heavy kernels' block size), each with its own side stream.
+    // Every piece runs its front kernels first, side by side with the others', then the heavy ones (chunk_count above); with more pieces
+    // than side streams (a forced setting) each piece simply runs its whole chain on stream k mod NAUX.
+    struct Piece { size_t first, cnt; };
     std::vector<Piece> pcs;
-    const size_t wave = wave_proofs_of(c);
     int chunks = chunk_count(c, m, vk->tune.overlap_chunks.load());
-    const bool piped = chunks == 1 && vk->tune.overlap_chunks.load() == 0 && m >= 2 * wave;
-    if (piped) {
-        size_t whole = m / wave * wave, rem = m - whole;
-        if (!worth_splitting(rem, wave)) { whole = m; rem = 0; }
-        if (rem) pcs.push_back({whole, rem, 2});
-        const size_t ww = (whole + wave - 1) / wave, npieces = (ww + 3) / 4;            // main pieces of at most four waves, evened out
-        const size_t per = wave * ((ww + npieces - 1) / npieces);
-        for (size_t f = 0; f < whole; f += per) pcs.push_back({f, std::min(per, whole - f), 1});
-    } else {
+    {
         size_t per = (m + chunks - 1) / chunks;
         per = (per + ZKV_HTPB - 1) / ZKV_HTPB * ZKV_HTPB;
-        for (size_t f = 0; f < m; f += per) pcs.push_back({f, std::min(per, m - f), 0});
+        for (size_t f = 0; f < m; f += per) pcs.push_back({f, std::min(per, m - f)});
     }
     const int np = (int)pcs.size();
     // pack(first, cnt, nullptr) returns the size of a piece's block, so every piece's region of the pinned staging buffer is known up front
@@ -501,23 +472,17 @@ static int host_pipeline(DevCtx* c, const zkv_vk* vk, size_t m, size_t in_bytes,
         for (int k = h + 1; k < np; k += H) { Sink sk{c->h_pin + offs[k], nullptr, nullptr, 0}; pack(pcs[k].first, pcs[k].cnt, &sk); ready[k].store(1, std::memory_order_release); }
     });
     if (!direct) { Sink sk{c->h_pin, nullptr, nullptr, 0}; pack(pcs[0].first, pcs[0].cnt, &sk); ready[0].store(1); }
-    // two pieces of a large batch (up to four whole waves + the partial one) are scheduled like chunks: own streams, fronts first, then the
-    // heavy kernels (one launch each) side by side, exactly as run_verify schedules the device-resident form of the same batch
-    const bool pair = piped && np == 2;
-    if (pair) { pcs[0].lane = pcs[1].lane = 0; }
-    const bool split = (!piped && np > 1 && np <= DevCtx::NAUX) || pair;
-    const bool pipe_copies = piped && !pair;
-    std::vector<cudaEvent_t> evs;                    // piped: upload-done and chain-done events per piece; split: front-done event per piece
-    if (pipe_copies || split) { evs.resize((pipe_copies ? 2 : 1) * (size_t)np, nullptr); for (auto& e : evs) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "cudaEventCreate"); }
+    const bool split = np > 1 && np <= DevCtx::NAUX;
+    std::vector<cudaEvent_t> evs;                    // front-done event per piece
+    if (split) { evs.resize((size_t)np, nullptr); for (auto& e : evs) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "cudaEventCreate"); }
     std::vector<Job> jobs(np);
-    auto kstream = [&](int k) { return pcs[k].lane == 1 ? c->stream : pcs[k].lane == 2 ? c->aux[2] : np == 1 ? c->stream : c->aux[k % DevCtx::NAUX]; };
+    auto kstream = [&](int k) { return np == 1 ? c->stream : c->aux[k % DevCtx::NAUX]; };
     for (int k = 0; k < np && !rc; k++) {
         const size_t first = pcs[k].first, cnt = pcs[k].cnt, in_off = offs[k];
-        cudaStream_t s = kstream(k), s_in = pipe_copies ? c->aux[0] : s, s_out = pipe_copies ? c->aux[1] : s;
+        cudaStream_t s = kstream(k), s_in = s, s_out = s;
         while (!ready[k].load(std::memory_order_acquire)) std::this_thread::yield();
         if (direct) { Sink sk{nullptr, c->d_in + in_off, s_in, 0}; pack(first, cnt, &sk); rc = sk.bad ? fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (page-locked caller memory to device)") : 0; }
         else rc = cudaMemcpyAsync(c->d_in + in_off, c->h_pin + in_off, bytes[k], cudaMemcpyHostToDevice, s_in) == cudaSuccess ? 0 : fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (host to device)");
-        if (!rc && pipe_copies && (cudaEventRecord(evs[2 * k], s_in) != cudaSuccess || cudaStreamWaitEvent(s, evs[2 * k], 0) != cudaSuccess)) rc = fail(ZKV_ERR_CUDA, "event (upload done)");
         if (rc) break;
         jobs[k] = job(first, cnt, c->d_in + in_off);
         if (split && !(jobs[k].all_fail || !vk->valid)) {
@@ -525,24 +490,20 @@ static int host_pipeline(DevCtx* c, const zkv_vk* vk, size_t m, size_t in_bytes,
             if (!rc && cudaEventRecord(evs[k], s) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "event (front done)");
             continue;
         }
-        rc = enqueue_chain(c, jobs[k], 0, first, (int)cnt, s, np == 1, piped);
-        if (!rc && pipe_copies && (cudaEventRecord(evs[2 * k + 1], s) != cudaSuccess || cudaStreamWaitEvent(s_out, evs[2 * k + 1], 0) != cudaSuccess)) rc = fail(ZKV_ERR_CUDA, "event (chain done)");
+        rc = enqueue_chain(c, jobs[k], 0, first, (int)cnt, s, np == 1);
         if (!rc && cudaMemcpyAsync(c->h_out + first, c->d_out + first, cnt, cudaMemcpyDeviceToHost, s_out) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (device to host)");
     }
     for (int k = 0; split && k < np && !rc; k++) {
         if (jobs[k].all_fail || !vk->valid) continue;        // (that piece ran its whole chain above)
         cudaStream_t s = kstream(k);
         for (int o = 0; o < np && !rc; o++) if (o != k && !(jobs[o].all_fail || !vk->valid) && cudaStreamWaitEvent(s, evs[o], 0) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "event wait (front done)");
-        if (!rc) rc = enqueue_chain(c, jobs[k], 0, pcs[k].first, (int)pcs[k].cnt, s, false, pair, 2);
+        if (!rc) rc = enqueue_chain(c, jobs[k], 0, pcs[k].first, (int)pcs[k].cnt, s, false, false, 2);
         if (!rc && cudaMemcpyAsync(c->h_out + pcs[k].first, c->d_out + pcs[k].first, pcs[k].cnt, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = fail(ZKV_ERR_CUDA, "cudaMemcpyAsync (device to host)");
     }
     for (auto& t : helpers) t.join();
     if (rc) { cudaDeviceSynchronize(); for (auto e : evs) if (e) cudaEventDestroy(e); return rc; }
     if (np == 1) { CK(cudaStreamSynchronize(c->stream)); collect_stage_ms(c); }
-    else {
-        for (int a = 0; a < DevCtx::NAUX; a++) CK(cudaStreamSynchronize(c->aux[a]));
-        if (piped) CK(cudaStreamSynchronize(c->stream));
-    }
+    else for (int a = 0; a < DevCtx::NAUX; a++) CK(cudaStreamSynchronize(c->aux[a]));
     for (auto e : evs) if (e) cudaEventDestroy(e);
     return 0;
 }

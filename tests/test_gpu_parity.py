@@ -475,7 +475,7 @@ def test_launch_counter_and_wave_size(Z, gpu, fx):
     assert Z.launch_count() - c0 == 6                      # one serial chain: decode, signals, vk_x, G2 check, Miller loop, final exponentiation
     n = 8192 + 300
     big = S.make_risc0_batch(gpu, vk, v.get_selector(), fx["control_root"], fx["bn254_control_id"], fx["sys0"], n, 0xB200000E, pool=8)
-    assert v.tune("overlap") == 0                          # default: automatic, half-wave chunks (SMs x 128 proofs) -> this batch is one chain
+    assert v.tune("overlap") == 0                          # default: automatic: one chain below half a wave (SMs x 128 proofs), four chunks above
     c0 = Z.launch_count()
     assert set(v.verify_batch(big.seals, big.image_ids, big.journals).tolist()) == {0}
     assert Z.launch_count() - c0 == 6
@@ -486,11 +486,11 @@ def test_launch_counter_and_wave_size(Z, gpu, fx):
     per_chain = 4 + segs + (4 if fe else 1)
     assert chunks == 4 and Z.launch_count() - c0 == chunks * per_chain
     v.tune("overlap", 0)
-    m = sms * 128 * 2 + 1                                  # just over two half-waves -> three chunks
+    m = sms * 128 + 1                                      # just over half a wave -> four chunks
     mid = S.make_risc0_batch(gpu, vk, v.get_selector(), fx["control_root"], fx["bn254_control_id"], fx["sys0"], m, 0xB200000F, pool=8)
     c0 = Z.launch_count()
     assert set(v.verify_batch(mid.seals, mid.image_ids, mid.journals).tolist()) == {0}
-    assert Z.launch_count() - c0 == 3 * per_chain
+    assert Z.launch_count() - c0 == 4 * per_chain
 
 
 def test_concurrent_calls_on_shared_and_separate_handles(Z, gpu, fx):
@@ -650,11 +650,10 @@ def test_campaign_batches_match_committed_oracle_digests(Z, gpu, consts):
 
 
 def test_large_batch_schedules_agree(Z, gpu, fx):
-    """Batches of two waves and more take other schedules than the four half-wave chunks of 2^16 proofs (csrc/zkv.cu chunk_count, run_verify,
-    host_pipeline): whole waves as one chain + the partial last wave beside it, and for host buffers pieces of up to four waves with pipelined
-    copies.  A mixed 6.4-wave batch through (a) the host-buffer call, (b) the device-resident call, (c) a forced 4-chunk host call and (d) a
-    forced single chain must give the same status bytes, equal to the generator's expectation everywhere and to the oracle on a sample; a
-    2.5-wave batch (two pieces scheduled like chunks) as well."""
+    """Large batches through every schedule the library has (csrc/zkv.cu chunk_count, run_verify, host_pipeline): a mixed 6.4-wave batch
+    through (a) the host-buffer call (automatic: four chunks, fronts first), (b) the device-resident call, (c) the same with page-locked
+    inputs uploaded in place, (d) a forced 7-chunk host call (more pieces than side streams) and (e) a forced single chain must give the same
+    status bytes, equal to the generator's expectation everywhere and to the oracle on a sample; a 2.5-wave batch as well."""
     import torch
     from stylus_zkvm_verifiers_b200 import synth as S
     wave = Z.wave_proofs(0, 0)
@@ -683,7 +682,7 @@ def test_large_batch_schedules_agree(Z, gpu, fx):
         poff = Z.pinned_copy(np.arange(n + 1, dtype=np.uint64) * 260)
         pinned = np.asarray(v.verify_batch_packed(pin[0], poff, pin[1], pin[2], n))
         assert (host == pinned).all()
-        v.tune("overlap", 4); forced4 = np.asarray(v.verify_batch(b.seals, b.image_ids, b.journals))
+        v.tune("overlap", 7); forced4 = np.asarray(v.verify_batch(b.seals, b.image_ids, b.journals))
         v.tune("overlap", 1); serial = np.asarray(v.verify_batch(b.seals, b.image_ids, b.journals))
         v.tune("overlap", 0)
         assert (host == dev).all() and (host == forced4).all() and (host == serial).all(), n
