@@ -196,6 +196,8 @@ int zkv_imad_peak(int device, double* wide_per_s, double* fpmul_per_s);
  * by a few host threads (one extra pass over the input in host memory).  Results are identical. */
 void* zkv_host_alloc(size_t bytes);
 void zkv_host_free(void* p);
+/* Test hook (no CUDA involved): the multi-threaded block copy the staging path uses for large input arrays. */
+void zkv_test_parallel_copy(void* dst, const void* src, size_t n);
 /* Known-answer self test of the production kernels on `device`: the reference's two golden proofs (the RISC Zero seal and the SP1 proof
  * of examples/{risc0,sp1}-verifier/examples/interact.rs, with the embedded keys of risc0/crypto.rs:16-79 and sp1/crypto.rs:7-81) must be
  * accepted and a one-bit tamper of each rejected with VerificationFailed, in both kernel layouts.  0 = pass, ZKV_ERR_STATE = a kernel

@@ -62,6 +62,7 @@ _SIGS = {
     "zkv_self_test": (C.c_int, [C.c_int]),
     "zkv_host_alloc": (C.c_void_p, [C.c_size_t]),
     "zkv_host_free": (None, [C.c_void_p]),
+    "zkv_test_parallel_copy": (None, [C.c_void_p, C.c_void_p, C.c_size_t]),
 }
 EXPORTS = tuple(_SIGS)
 

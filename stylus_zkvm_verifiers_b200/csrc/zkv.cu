@@ -803,6 +803,7 @@ extern "C" int zkv_sp1_verify_batch_device(const zkv_sp1* h, int device, const v
 }
 
 
+extern "C" void zkv_test_parallel_copy(void* dst, const void* src, size_t n) { pcopy(dst, src, n); }
 extern "C" void* zkv_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (zkv_device_count() <= 0 || cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); fail(ZKV_ERR_CUDA, "zkv_host_alloc: cudaHostAlloc failed"); return nullptr; }
